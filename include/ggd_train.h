@@ -1,0 +1,130 @@
+/*
+ * ggd_train.h -- C ABI of the B200-native drop-in for the reference's BP_GPU class
+ * (Train_code_ML_GGD/BP_GPU.h:45-70), i.e. the device path of BPtrain_Sigmoid:
+ * forward -> GGD / beta-norm loss gradient -> backward -> momentum SGD, plus the three
+ * cross-validation metrics.  Plain pointers and sizes only; every entry point returns 0 on
+ * success or a negative GGD_E* code (ggd_last_error() gives the text).  There is no CPU
+ * fallback: every call fails with GGD_ECUDA when no sm_100 device is usable.
+ *
+ * Entry point                  replaces (reference file:line)
+ * ---------------------------  -------------------------------------------------------------
+ * ggd_create                   BP_GPU::BP_GPU               BP_GPU.cu:9-113
+ * ggd_destroy                  BP_GPU::~BP_GPU              BP_GPU.cu:115-150
+ * ggd_train                    BP_GPU::train                BP_GPU.cu:152-185  (+ train_bunch_single :308-440)
+ * ggd_cv_sqerr                 BP_GPU::CrossValid           BP_GPU.cu:187-221
+ * ggd_cv_abserr                BP_GPU::CrossValiddB         BP_GPU.cu:222-255
+ * ggd_cv_loglik                BP_GPU::CrossValid2 + Gamma  BP_GPU.cu:256-306, 593-640
+ * ggd_get_weights              BP_GPU::returnWeights        BP_GPU.cu:514-525
+ *
+ * Layouts are the reference's: `in` is n_frames x layersizes[0] row-major (already z-scored,
+ * context-expanded, shuffled: Interface.cc:719-838), `targ` is n_frames x layersizes[last],
+ * weights[l] (l = 1..numlayers-1) is float[layersizes[l]*layersizes[l-1]] with
+ * index = out + in*layersizes[l] (the .wts / MATLAB order, DevFunc.h:65-75), bias[l] is
+ * float[layersizes[l]].  Index 0 of the weights/bias pointer arrays is unused, as in the reference.
+ * The caller owns every host array; the library copies in and out.
+ */
+#ifndef GGD_TRAIN_H_
+#define GGD_TRAIN_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGD_MAXLAYER 10          /* BP_GPU.h:6 */
+#define GGD_MAXCACHEFRAME 200000 /* BP_GPU.h:7: upper bound on n_frames per call */
+
+enum {
+    GGD_OK = 0,
+    GGD_EINVAL = -1,   /* bad argument / unsupported configuration */
+    GGD_ECUDA = -2,    /* CUDA runtime or driver error, or no sm_100 device */
+    GGD_ENOMEM = -3,
+    GGD_ENCCL = -4,
+    GGD_EUNSUPPORTED = -5
+};
+
+/* arithmetic used for the dense contractions */
+enum {
+    GGD_PREC_BF16X3 = 0,  /* default: tcgen05 kind::f16, every fp32 operand split into bf16 hi+lo,
+                             3 MMAs (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM */
+    GGD_PREC_FP32_SIMT = 1 /* validation path: plain fp32 FMA GEMMs on CUDA cores (slow) */
+};
+
+typedef struct ggd_config {
+    int   numlayers;                  /* <= GGD_MAXLAYER, counts the input layer */
+    int   layersizes[GGD_MAXLAYER];
+    int   bunchsize;                  /* frames per minibatch ON THIS RANK */
+    float lrate, momentum, weightcost;
+    float shapefactor;                /* beta */
+    int   MLflag;                     /* 1: GGD maximum-likelihood gradient; else beta-norm */
+    int   dropoutflag;                /* must be 0 (dropout is outside the named path) */
+    float visible_omit, hid_omit;     /* accepted, unused while dropoutflag == 0 */
+    int   gpu;                        /* CUDA device ordinal (gpu_used=) */
+    int   seed;                       /* accepted for signature parity (only seeds dropout in the reference) */
+    int   precision;                  /* GGD_PREC_* */
+    /* frame-sharded data parallelism; world_size <= 1 means single GPU */
+    int   world_size, rank;
+    const void *nccl_unique_id;       /* 128-byte ncclUniqueId shared by all ranks, or NULL */
+    int   flags;                      /* GGD_FLAG_* */
+} ggd_config;
+
+enum {
+    GGD_FLAG_UNFUSED_UPDATE = 1,  /* materialise the weight gradient and run the stand-alone update kernel
+                                     (always the case when world_size > 1) */
+    GGD_FLAG_NO_GRAPH = 2,        /* launch kernels directly instead of replaying a CUDA graph */
+    GGD_FLAG_KEEP_DEBUG = 4,      /* keep per-step tensors readable through ggd_debug_read */
+    GGD_FLAG_PIN_HOST = 8         /* cudaHostRegister the caller's (long-lived, reused) chunk buffers on first use;
+                                     the reference's Interface allocates them once (Interface.cc:476-480) */
+};
+
+typedef struct ggd_handle ggd_handle;
+
+int ggd_create(const ggd_config *cfg, const float *const *weights, const float *const *bias, ggd_handle **out);
+int ggd_destroy(ggd_handle *h);
+
+/* One call = one chunk: H2D copy, then one training step per full bunch; a trailing partial bunch is
+ * dropped (BP_GPU.cu:173-180).  Blocking, like the reference. */
+int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ);
+/* Same, for a chunk that is already resident in device memory (fp32, same layouts). */
+int ggd_train_device(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ);
+
+int ggd_cv_sqerr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result);
+int ggd_cv_abserr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result);
+int ggd_cv_loglik(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result);
+/* forward only: out is n_frames x layersizes[last] (cv_bunch_single, BP_GPU.cu:442-512) */
+int ggd_forward(ggd_handle *h, int n_frames, const float *in, float *out);
+
+int ggd_get_weights(ggd_handle *h, float *const *weights, float *const *bias);
+/* GGD scale factors alpha_d left by the last training bunch (dev.scalefactor) */
+int ggd_get_alpha(ggd_handle *h, float *alpha);
+/* per-bunch loss trace of the last ggd_train* call (SURVEY.md 8c definition); *n = bunches run */
+int ggd_get_losses(ggd_handle *h, float *losses, int max, int *n);
+
+/* timing / accounting of the last ggd_train* call */
+typedef struct ggd_stats {
+    double device_ms;        /* CUDA-event time of the training steps on the compute stream */
+    double h2d_ms;           /* CUDA-event time of the chunk upload (0 for ggd_train_device) */
+    long long launches;      /* kernels launched (graph nodes count individually) */
+    long long steps;         /* bunches trained */
+    long long h2d_bytes, d2h_bytes;
+} ggd_stats;
+int ggd_get_stats(ggd_handle *h, ggd_stats *s);
+
+/* Parity hooks (tests only): run ONE bunch with or without applying the update, then read tensors.
+ * what: 0 = out [M][D], 1 = dedx of layer l [M][units], 2 = y of layer l, 3 = weight gradient of
+ * layer l (reference order out + in*cur), 4 = bias gradient of layer l. */
+int ggd_debug_step(ggd_handle *h, int n_frames, const float *in, const float *targ, int apply_update);
+int ggd_debug_read(ggd_handle *h, int what, int layer, float *dst);
+
+/* Raw tcgen05 GEMM probe (tests only): D[i][j] = sum_r A(i,r) B(j,r), fp32 host arrays.
+ * a_mn / b_mn = 0: operand is [rows][R] (reduction contiguous); 1: operand is [R][rows]. */
+int ggd_debug_gemm(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, const float *A, const float *B, float *D);
+/* writes a 128-byte ncclUniqueId (rank 0 creates it, every rank passes it in ggd_config) */
+int ggd_nccl_unique_id(void *out128);
+
+const char *ggd_last_error(void);
+const char *ggd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

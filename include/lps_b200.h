@@ -1,0 +1,60 @@
+/*
+ * lps_b200.h -- C ABI of the B200-native log-power-spectrum (LPS) front end, the drop-in for the
+ * arithmetic of the reference's Wav2LPS_be at 16 kHz
+ * (Feature_prepare/SourceCode_Wav2LogSpec_be/Wav2LogSpec_be.c:395-404, 413-576; FEfunc.c:80-118, 146-293;
+ *  fileio.c:231-243, 268-282): int16 PCM -> 512-sample frames every 256 samples -> Hamming window ->
+ * 512-point real split-radix FFT -> power -> floored natural log -> 257 bins per frame.
+ *
+ * The kernel executes the reference's butterfly network itself (same operations, same order within each
+ * butterfly, no FMA contraction), so features are bit-identical to the reference except where the
+ * double-precision log of the GPU differs from glibc's in the last place.
+ *
+ * Entry point               replaces
+ * ------------------------  ---------------------------------------------------------------------
+ * lps_nframes               frame count implied by the main loop, Wav2LogSpec_be.c:401-416
+ * lps_extract               main frame loop for one utterance (host buffers)
+ * lps_extract_batch         the same for many utterances in one launch (host buffers)
+ * lps_extract_batch_device  the same with device-resident PCM / features
+ * Output options (flags) cover the two consumers of the features: the HTK writer
+ * (big-endian floats, fileio.c:231-243) and the trainer's z-score with the reciprocal-std .norm
+ * file (Interface.cc:760-766).
+ */
+#ifndef LPS_B200_H_
+#define LPS_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPS_BINS 257
+#define LPS_FRAME_LEN 512
+#define LPS_FRAME_SHIFT 256
+
+enum {
+    LPS_FLAG_BIG_ENDIAN = 1,  /* byte-swap each float (ready for fwrite into an HTK file) */
+    LPS_FLAG_ZSCORE = 2       /* (x - mean[k]) * dvar[k] with the .norm constants; not combinable with BIG_ENDIAN */
+};
+
+typedef struct lps_handle lps_handle;
+
+long lps_nframes(long n_samples);
+int lps_create(int gpu, lps_handle **out);
+int lps_destroy(lps_handle *h);
+/* mean / dvar: 257 floats each (host), needed for LPS_FLAG_ZSCORE */
+int lps_set_norm(lps_handle *h, const float *mean, const float *dvar);
+
+/* one utterance, host in / host out; out must hold lps_nframes(n_samples) * 257 floats */
+int lps_extract(lps_handle *h, const int16_t *pcm, long n_samples, float *out, int flags);
+/* utt_off: n_utts + 1 sample offsets into pcm (host). Frames of utterance u follow those of u-1 in out.
+ * total_frames (optional) receives the frame count. */
+int lps_extract_batch(lps_handle *h, const int16_t *pcm, const long *utt_off, int n_utts, float *out, int flags, long *total_frames);
+/* device-resident variant; utt_off stays a host array. d_out must hold sum_u lps_nframes(len_u) * 257 floats */
+int lps_extract_batch_device(lps_handle *h, const int16_t *d_pcm, const long *utt_off, int n_utts, float *d_out, int flags, long *total_frames);
+/* CUDA-event time (ms) of the kernel(s) of the last call */
+double lps_last_kernel_ms(lps_handle *h);
+const char *lps_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,348 @@
+// gemm_tc.cu -- tcgen05 / TMEM / TMA GEMM kernel (see gemm_tc.cuh for the operand conventions).
+//
+// CTA = 192 threads: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  Output tile 128 x BN, reduction in 64-element
+// blocks through a 3/4-stage mbarrier ring.  The reduction can be split over a thread-block cluster of
+// S CTAs (gridDim.x = S): every CTA accumulates its share of the k-blocks in its own TMEM, then the
+// partial tiles are reduce-scattered through distributed shared memory (CTA r owns columns
+// [r*BN/S, (r+1)*BN/S)), summed in a fixed order, and only then the epilogue runs -- no partial sums
+// ever touch L2/HBM and the result is deterministic.
+#include "gemm_tc.cuh"
+#include "../../include/ggd_train.h"
+#include <cudaTypedefs.h>
+
+namespace ggd {
+
+constexpr int BK = 64;                 // reduction elements per stage (128 bytes of bf16: one swizzle row)
+constexpr int TILE_I = 128;            // UMMA M
+constexpr int A_TILE = TILE_I * BK * 2;
+constexpr int NTHREADS = 192;
+
+template <int BN> struct TileCfg {
+    static constexpr int B_TILE = BN * BK * 2;
+    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    static constexpr int SMEM = STAGES * STAGE + 1024;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t raddr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ---- epilogues: 16 consecutive output columns [j, j+16) of output row i ----------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue16(const GemmArgs &g, int i, int j, float *v)
+{
+    const bool row_ok = i < g.I;
+    if constexpr (EPI == EPI_STORE_F32) {
+        if (!row_ok) return;
+        float4 *dst = reinterpret_cast<float4 *>(g.o32 + (size_t)i * g.ld32 + j);
+#pragma unroll
+        for (int q = 0; q < 4; q++) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else if constexpr (EPI == EPI_FWD_LINEAR) {
+        float4 *dst = reinterpret_cast<float4 *>(g.o32 + (size_t)i * g.ld32 + j);
+        const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + j);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 b = __ldg(b4 + q);
+            float4 o;
+            o.x = (row_ok && j + 4 * q + 0 < g.J) ? v[4 * q + 0] + b.x : 0.0f;
+            o.y = (row_ok && j + 4 * q + 1 < g.J) ? v[4 * q + 1] + b.y : 0.0f;
+            o.z = (row_ok && j + 4 * q + 2 < g.J) ? v[4 * q + 2] + b.z : 0.0f;
+            o.w = (row_ok && j + 4 * q + 3 < g.J) ? v[4 * q + 3] + b.w : 0.0f;
+            dst[q] = o;
+        }
+    } else {
+        float r[16];
+        if constexpr (EPI == EPI_FWD_SIGMOID) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const float x = v[e] + __ldg(g.bias + j + e);
+                r[e] = (row_ok && j + e < g.J) ? 1.0f / (1.0f + expf(-x)) : 0.0f;   // kernSigmoid, DevFunc.cu:36-51
+            }
+        } else {  // EPI_DX_DSIGMOID
+            const uint4 *yh = reinterpret_cast<const uint4 *>(g.y_hi + (size_t)i * g.ldy + j);
+            const uint4 *yl = reinterpret_cast<const uint4 *>(g.y_lo + (size_t)i * g.ldy + j);
+            uint32_t h[8], l[8];
+            *reinterpret_cast<uint4 *>(h) = __ldg(yh);
+            *reinterpret_cast<uint4 *>(h + 4) = __ldg(yh + 1);
+            *reinterpret_cast<uint4 *>(l) = __ldg(yl);
+            *reinterpret_cast<uint4 *>(l + 4) = __ldg(yl + 1);
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const uint32_t hw = h[e >> 1], lw = l[e >> 1];
+                const float yhi = __uint_as_float((e & 1) ? (hw & 0xFFFF0000u) : (hw << 16));
+                const float ylo = __uint_as_float((e & 1) ? (lw & 0xFFFF0000u) : (lw << 16));
+                const float y = yhi + ylo;
+                r[e] = (row_ok && j + e < g.J) ? (1.0f - y) * y * v[e] : 0.0f;      // kernDsigmoid, DevFunc.cu:53-71
+            }
+        }
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            bf16 h0, l0, h1, l1;
+            split_bf16(r[2 * e], h0, l0);
+            split_bf16(r[2 * e + 1], h1, l1);
+            ph[e] = pack_bf16x2(h0, h1);
+            pl[e] = pack_bf16x2(l0, l1);
+        }
+        uint4 *oh = reinterpret_cast<uint4 *>(g.o_hi + (size_t)i * g.ldo + j);
+        uint4 *ol = reinterpret_cast<uint4 *>(g.o_lo + (size_t)i * g.ldo + j);
+        oh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        oh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        ol[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        ol[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmArgs g)
+{
+    using Cfg = TileCfg<BN>;
+    constexpr int B_TILE = Cfg::B_TILE, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = gridDim.x, rank = blockIdx.x;          // cluster = the gridDim.x CTAs that share one output tile
+    const int j0 = blockIdx.y * BN, i0 = blockIdx.z * TILE_I;
+    const int kb0 = (g.kblocks * rank) / S, kb1 = (g.kblocks * (rank + 1)) / S;
+    const int nkb = kb1 - kb0;
+    const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
+        tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            mbar_init(&tmem_full_bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<BN>(&tmem_base_s);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], STAGE);
+                uint8_t *st = smem + s * STAGE;
+                const int r0 = (kb0 + it) * BK;
+                if constexpr (!A_MN) {
+                    tma_load_2d(st, &tm_a_hi, &full_bar[s], r0, i0 + a_row_off);
+                    tma_load_2d(st + A_TILE, &tm_a_lo, &full_bar[s], r0, i0 + a_row_off);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        tma_load_2d(st + h * 8192, &tm_a_hi, &full_bar[s], i0 + 64 * h, r0 + a_row_off);
+                        tma_load_2d(st + A_TILE + h * 8192, &tm_a_lo, &full_bar[s], i0 + 64 * h, r0 + a_row_off);
+                    }
+                }
+                uint8_t *sb = st + 2 * A_TILE;
+                if constexpr (!B_MN) {
+                    tma_load_2d(sb, &tm_b_hi, &full_bar[s], r0, j0);
+                    tma_load_2d(sb + B_TILE, &tm_b_lo, &full_bar[s], r0, j0);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < BN / 64; h++) {
+                        tma_load_2d(sb + h * 8192, &tm_b_hi, &full_bar[s], j0 + 64 * h, r0);
+                        tma_load_2d(sb + B_TILE + h * 8192, &tm_b_lo, &full_bar[s], j0 + 64 * h, r0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_I, BN, A_MN, B_MN);
+            constexpr uint32_t A_LBO = A_MN ? 8192u : 16u, B_LBO = B_MN ? 8192u : 16u;
+            constexpr uint32_t A_KSTEP = A_MN ? 2048u : 32u, B_KSTEP = B_MN ? 2048u : 32u;
+            for (int it = 0; it < nkb; it++) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * STAGE), a_lo = a_hi + A_TILE;
+                const uint32_t b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) {
+                    const uint64_t dah = make_smem_desc(a_hi + k * A_KSTEP, A_LBO, 1024);
+                    const uint64_t dal = make_smem_desc(a_lo + k * A_KSTEP, A_LBO, 1024);
+                    const uint64_t dbh = make_smem_desc(b_hi + k * B_KSTEP, B_LBO, 1024);
+                    const uint64_t dbl = make_smem_desc(b_lo + k * B_KSTEP, B_LBO, 1024);
+                    umma_bf16(tmem, dal, dbh, idesc, (it | k) != 0);   // small terms first
+                    umma_bf16(tmem, dah, dbl, idesc, 1);
+                    umma_bf16(tmem, dah, dbh, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs retire
+            }
+            umma_commit(&tmem_full_bar);
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps: wait for the accumulator =====
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+    }
+
+    const int q = warp & 3;                 // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;          // output row inside the tile
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const int W = BN / S;                   // columns owned by each CTA of the cluster
+    float *recv = reinterpret_cast<float *>(smem);   // [S][128][W], aliases the (drained) pipeline stages
+
+    if (S > 1) {
+        cluster_sync_all();   // every CTA of the cluster has retired its MMAs: stage memory is free everywhere
+        if (warp >= 2) {
+            for (int p = 0; p < S; p++) {
+                if (p == rank) continue;
+                for (int c = 0; c < W; c += 16) {
+                    float v[16];
+                    tmem_ld16(trow + p * W + c, v);
+                    const uint32_t dst = map_to_cta(smem_u32(recv + ((size_t)rank * TILE_I + row) * W + c), p);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) st_cluster_f4(dst + 16 * e, v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                }
+            }
+        }
+        cluster_sync_all();   // all partial slabs have landed
+    }
+    if (warp >= 2) {
+        for (int c = 0; c < W; c += 16) {
+            float v[16];
+            tmem_ld16(trow + rank * W + c, v);
+            for (int p = 0; p < S; p++) {
+                if (p == rank) continue;
+                const float4 *src = reinterpret_cast<const float4 *>(recv + ((size_t)p * TILE_I + row) * W + c);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float4 t = src[e];
+                    v[4 * e] += t.x; v[4 * e + 1] += t.y; v[4 * e + 2] += t.z; v[4 * e + 3] += t.w;
+                }
+            }
+            epilogue16<EPI>(g, i0 + row, j0 + rank * W + c, v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<BN>(tmem);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int make_tmap_bf16(CUtensorMap *m, const bf16 *base, long long rows, long long cols, long long ld, int box_rows)
+{
+    if (!g_encode) { set_error("tensor-map encoder not initialised"); return GGD_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16 *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld); return GGD_ECUDA; }
+    return GGD_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_inst(const GemmPlan &p, cudaStream_t s)
+{
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.splits, p.tiles_j, p.tiles_i);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = TileCfg<BN>::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = p.splits; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GGD_CUDA(cudaLaunchKernelEx(&cfg, kern, p.a_hi, p.a_lo, p.b_hi, p.b_lo, p.args));
+    return GGD_OK;
+}
+
+template <int BN>
+static int launch_bn(const GemmPlan &p, cudaStream_t s)
+{
+    const int key = p.a_mn * 100 + p.b_mn * 10 + p.epi;
+    switch (key) {
+    case 10 + EPI_FWD_SIGMOID: return launch_inst<BN, false, true, EPI_FWD_SIGMOID>(p, s);
+    case 10 + EPI_FWD_LINEAR:  return launch_inst<BN, false, true, EPI_FWD_LINEAR>(p, s);
+    case 10 + EPI_STORE_F32:   return launch_inst<BN, false, true, EPI_STORE_F32>(p, s);
+    case 0 + EPI_DX_DSIGMOID:  return launch_inst<BN, false, false, EPI_DX_DSIGMOID>(p, s);
+    case 0 + EPI_STORE_F32:    return launch_inst<BN, false, false, EPI_STORE_F32>(p, s);
+    case 110 + EPI_STORE_F32:  return launch_inst<BN, true, true, EPI_STORE_F32>(p, s);
+    default: set_error("gemm_tc: unsupported variant a_mn=%d b_mn=%d epi=%d", p.a_mn, p.b_mn, p.epi); return GGD_EINVAL;
+    }
+}
+
+int launch_gemm_tc(const GemmPlan &p, cudaStream_t s)
+{
+    if (p.splits < 1 || p.splits > 8 || (p.bn / p.splits) % 16 != 0 || p.splits > p.args.kblocks) {
+        set_error("gemm_tc: bad split %d for bn=%d kblocks=%d", p.splits, p.bn, p.args.kblocks);
+        return GGD_EINVAL;
+    }
+    if (p.bn == 128) return launch_bn<128>(p, s);
+    if (p.bn == 64) return launch_bn<64>(p, s);
+    set_error("gemm_tc: bn must be 64 or 128");
+    return GGD_EINVAL;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int prep_inst()
+{
+    GGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::SMEM));
+    return GGD_OK;
+}
+template <int BN>
+static int prep_bn()
+{
+    int rc;
+    if ((rc = prep_inst<BN, false, true, EPI_FWD_SIGMOID>())) return rc;
+    if ((rc = prep_inst<BN, false, true, EPI_FWD_LINEAR>())) return rc;
+    if ((rc = prep_inst<BN, false, true, EPI_STORE_F32>())) return rc;
+    if ((rc = prep_inst<BN, false, false, EPI_DX_DSIGMOID>())) return rc;
+    if ((rc = prep_inst<BN, false, false, EPI_STORE_F32>())) return rc;
+    if ((rc = prep_inst<BN, true, true, EPI_STORE_F32>())) return rc;
+    return GGD_OK;
+}
+
+int gemm_tc_init()
+{
+    // per-device function attributes (cheap; repeated calls are harmless)
+    int rc;
+    if ((rc = prep_bn<64>())) return rc;
+    if ((rc = prep_bn<128>())) return rc;
+    if (g_encode) return GGD_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GGD_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled not available"); return GGD_ECUDA; }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return GGD_OK;
+}
+
+}  // namespace ggd

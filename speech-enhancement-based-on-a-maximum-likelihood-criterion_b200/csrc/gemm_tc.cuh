@@ -1,0 +1,57 @@
+// gemm_tc.cuh -- the tcgen05 / TMEM / TMA GEMM of the training step.
+//
+// One kernel template serves the three dense contractions of BP_GPU::train_bunch_single
+// (BP_GPU.cu:361 SgemmNN, :430 SgemmTN, :432 SgemmNT), written as
+//        D[i][j] = sum_r A(i,r) * B(j,r)            (tile: 128 rows i  x  BN columns j)
+// with each operand either K-major (r contiguous in memory) or MN-major (i / j contiguous):
+//   forward   x[m][n]   = sum_k y[m][k] W[k][n]      A = y    K-major   B = W     MN-major
+//   backward  dy[m][k]  = sum_n dx[m][n] W[k][n]     A = dx   K-major   B = W     K-major
+//   gradient  g[k][n]   = sum_m y[m][k] dx[m][n]     A = y    MN-major  B = dx    MN-major
+// so the weight matrix is never transposed in memory (it keeps the reference's .wts order).
+//
+// Arithmetic: every fp32 operand is stored as a bf16 pair (hi, lo); a product is formed as
+// hi*hi + hi*lo + lo*hi by three kind::f16 MMAs into one fp32 TMEM accumulator (bf16x3).
+#pragma once
+#include "kernels.cuh"
+
+namespace ggd {
+
+enum GemmEpilogue {
+    EPI_FWD_SIGMOID = 0,  // + bias, sigmoid, write bf16 hi/lo activations (kernMultiCopy + kernSigmoid fused)
+    EPI_FWD_LINEAR = 1,   // + bias, write fp32 network output
+    EPI_DX_DSIGMOID = 2,  // * y(1-y), write bf16 hi/lo dE/dx of the previous layer (kernDsigmoid fused)
+    EPI_STORE_F32 = 3     // plain fp32 store (weight gradient)
+};
+
+struct GemmArgs {
+    const StepCtl *ctl;
+    int a_rows_from_ctl;   // add ctl->bunch_idx * rows_per_bunch to the ROW coordinate of A's tensor map
+    int rows_per_bunch;
+    int I, J;              // valid output extent; rows >= I or columns >= J are written as zeros
+    int kblocks;           // reduction length / 64
+    const float *bias;     // EPI_FWD_*
+    bf16 *o_hi, *o_lo;     // bf16 outputs, pitch ldo
+    int ldo;
+    float *o32;            // fp32 output, pitch ld32
+    int ld32;
+    const bf16 *y_hi, *y_lo;  // EPI_DX_DSIGMOID: activations of the layer whose dE/dx is produced, pitch ldy
+    int ldy;
+};
+
+struct GemmPlan {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    GemmArgs args;
+    int bn;          // 64 or 128
+    int a_mn, b_mn;  // operand majors
+    int epi;
+    int splits;      // cluster size along the reduction (1, 2, 4 or 8)
+    int tiles_i, tiles_j;
+};
+
+// 2-D bf16 row-major tensor [rows][cols] (pitch ld elements) with a {64, box_rows} box, 128-byte swizzle
+int make_tmap_bf16(CUtensorMap *m, const bf16 *base, long long rows, long long cols, long long ld, int box_rows);
+
+int launch_gemm_tc(const GemmPlan &p, cudaStream_t s);
+int gemm_tc_init();   // resolves the driver entry point, sets the shared-memory attributes
+
+}  // namespace ggd

@@ -1,0 +1,758 @@
+// ggd_train.cu -- the C ABI of libggd_b200 (include/ggd_train.h): device workspace, chunk upload,
+// the per-bunch training step (captured once as a CUDA graph and replayed for every bunch of a chunk),
+// cross-validation forward passes and weight export.
+//
+// Reference behaviour restated (not ported): Train_code_ML_GGD/BP_GPU.cu.  Differences by design:
+//   * 53 launches + 5 host syncs per bunch become one graph replay per 16 bunches;
+//   * cuBLAS fp32 SGEMM becomes the tcgen05 bf16x3 GEMM of gemm_tc.cu (no cuBLAS anywhere);
+//   * the 11-kernel loss chain is one kernel; the 4-launch-per-layer update is one launch per step;
+//   * all weights live in one padded arena so that update / allreduce are single flat passes.
+#include "../../include/ggd_train.h"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include <nccl.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <map>
+
+namespace ggd {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+}  // namespace ggd
+
+using namespace ggd;
+
+#define GGD_NCCL(expr)                                                                            \
+    do {                                                                                          \
+        ncclResult_t _r = (expr);                                                                 \
+        if (_r != ncclSuccess) {                                                                  \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, ncclGetErrorString(_r));      \
+            return GGD_ENCCL;                                                                     \
+        }                                                                                         \
+    } while (0)
+#define GGD_TRY(expr)              \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != GGD_OK) return _rc; \
+    } while (0)
+
+struct LayerInfo {
+    int prev, cur;      // real units
+    int Kp, Np;         // padded units (multiples of 64)
+    size_t w_off, b_off;  // element offsets in the parameter arenas
+};
+
+struct ggd_handle {
+    ggd_config cfg;
+    int L, M, Mp, Mg, sm_count;
+    int units[GGD_MAXLAYER], upad[GGD_MAXLAYER];
+    LayerInfo lay[GGD_MAXLAYER];
+    bool tensor;        // GGD_PREC_BF16X3
+    // parameter arenas (same element offsets in each)
+    size_t arena;
+    float *P, *Dl, *G;
+    bf16 *Phi, *Plo;
+    // per-layer activations / gradients of one bunch
+    bf16 *act_hi[GGD_MAXLAYER], *act_lo[GGD_MAXLAYER], *dx_hi[GGD_MAXLAYER], *dx_lo[GGD_MAXLAYER];
+    float *x32[GGD_MAXLAYER], *y32[GGD_MAXLAYER], *dy32[GGD_MAXLAYER], *dx32[GGD_MAXLAYER];
+    float *out32;       // [Mp][upad[L-1]]
+    float *alpha, *colsum;
+    double *trace;
+    size_t trace_cap;
+    StepCtl *ctl;
+    // chunk staging
+    float *c_in, *c_targ, *c_out;
+    bf16 *c_hi, *c_lo;
+    size_t cap;         // frames
+    std::map<const void *, size_t> pinned;
+    cudaStream_t s_main;
+    cudaEvent_t ev0, ev1, ev2;
+    // plans + graphs
+    GemmPlan fwd[GGD_MAXLAYER], dxp[GGD_MAXLAYER], dwp[GGD_MAXLAYER];
+    cudaGraphExec_t g1, gN;
+    int gN_steps;
+    int launches_per_step;
+    // DP
+    ncclComm_t comm;
+    bool has_comm;
+    // host mirrors / stats
+    std::vector<float> losses;
+    std::vector<float> h_out;
+    ggd_stats stats;
+};
+
+static void free_chunk(ggd_handle *h)
+{
+    cudaFree(h->c_in); cudaFree(h->c_targ); cudaFree(h->c_out); cudaFree(h->c_hi); cudaFree(h->c_lo); cudaFree(h->trace);
+    h->c_in = h->c_targ = h->c_out = nullptr; h->c_hi = h->c_lo = nullptr; h->trace = nullptr;
+    h->cap = 0;
+    if (h->g1) { cudaGraphExecDestroy(h->g1); h->g1 = nullptr; }
+    if (h->gN) { cudaGraphExecDestroy(h->gN); h->gN = nullptr; }
+}
+
+static int pick_splits(int tiles, int bn, int kblocks, int sm)
+{
+    int best = 1;
+    for (int s = 2; s <= 8; s *= 2)
+        if (s <= kblocks && (bn / s) % 16 == 0 && tiles * s <= sm + sm / 8) best = s;
+    return best;
+}
+
+// (re)build tensor maps and GEMM plans; needs the chunk buffers for the layer-1 operands
+static int build_plans(ggd_handle *h)
+{
+    const int L = h->L;
+    for (int l = 1; l < L; l++) {
+        const LayerInfo &ly = h->lay[l];
+        const bool first = (l == 1), last = (l == L - 1);
+        const bf16 *ah = first ? h->c_hi : h->act_hi[l - 1], *al = first ? h->c_lo : h->act_lo[l - 1];
+        const long long arows = first ? (long long)h->cap : h->Mp;
+        // ---- forward: x[m][n] = sum_k y[m][k] W[k][n]
+        {
+            GemmPlan &p = h->fwd[l];
+            memset(&p, 0, sizeof p);
+            p.bn = (ly.Np % 128 == 0) ? 128 : 64;
+            p.a_mn = 0; p.b_mn = 1;
+            p.epi = last ? EPI_FWD_LINEAR : EPI_FWD_SIGMOID;
+            p.tiles_i = h->Mp / 128; p.tiles_j = ly.Np / p.bn;
+            GGD_TRY(make_tmap_bf16(&p.a_hi, ah, arows, ly.Kp, ly.Kp, 128));
+            GGD_TRY(make_tmap_bf16(&p.a_lo, al, arows, ly.Kp, ly.Kp, 128));
+            GGD_TRY(make_tmap_bf16(&p.b_hi, h->Phi + ly.w_off, ly.Kp, ly.Np, ly.Np, 64));
+            GGD_TRY(make_tmap_bf16(&p.b_lo, h->Plo + ly.w_off, ly.Kp, ly.Np, ly.Np, 64));
+            GemmArgs &a = p.args;
+            a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
+            a.I = h->M; a.J = ly.cur; a.kblocks = ly.Kp / 64;
+            a.bias = h->P + ly.b_off;
+            a.o_hi = h->act_hi[l]; a.o_lo = h->act_lo[l]; a.ldo = ly.Np;
+            a.o32 = h->out32; a.ld32 = ly.Np;
+            p.splits = pick_splits(p.tiles_i * p.tiles_j, p.bn, a.kblocks, h->sm_count);
+        }
+        // ---- backward: dE/dy[m][k] = sum_n dE/dx[m][n] W[k][n], times y(1-y) of layer l-1
+        if (!first) {
+            GemmPlan &p = h->dxp[l];
+            memset(&p, 0, sizeof p);
+            p.bn = (ly.Kp % 128 == 0) ? 128 : 64;
+            p.a_mn = 0; p.b_mn = 0;
+            p.epi = EPI_DX_DSIGMOID;
+            p.tiles_i = h->Mp / 128; p.tiles_j = ly.Kp / p.bn;
+            GGD_TRY(make_tmap_bf16(&p.a_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 128));
+            GGD_TRY(make_tmap_bf16(&p.a_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 128));
+            GGD_TRY(make_tmap_bf16(&p.b_hi, h->Phi + ly.w_off, ly.Kp, ly.Np, ly.Np, p.bn));
+            GGD_TRY(make_tmap_bf16(&p.b_lo, h->Plo + ly.w_off, ly.Kp, ly.Np, ly.Np, p.bn));
+            GemmArgs &a = p.args;
+            a.ctl = h->ctl; a.a_rows_from_ctl = 0; a.rows_per_bunch = h->M;
+            a.I = h->M; a.J = ly.prev; a.kblocks = ly.Np / 64;
+            a.o_hi = h->dx_hi[l - 1]; a.o_lo = h->dx_lo[l - 1]; a.ldo = ly.Kp;
+            a.y_hi = h->act_hi[l - 1]; a.y_lo = h->act_lo[l - 1]; a.ldy = ly.Kp;
+            p.splits = pick_splits(p.tiles_i * p.tiles_j, p.bn, a.kblocks, h->sm_count);
+        }
+        // ---- gradient: g[k][n] = sum_m y[m][k] dE/dx[m][n]
+        {
+            GemmPlan &p = h->dwp[l];
+            memset(&p, 0, sizeof p);
+            p.bn = (ly.Np % 128 == 0) ? 128 : 64;
+            p.a_mn = 1; p.b_mn = 1;
+            p.epi = EPI_STORE_F32;
+            p.tiles_i = ceil_div(ly.Kp, 128); p.tiles_j = ly.Np / p.bn;
+            GGD_TRY(make_tmap_bf16(&p.a_hi, ah, arows, ly.Kp, ly.Kp, 64));
+            GGD_TRY(make_tmap_bf16(&p.a_lo, al, arows, ly.Kp, ly.Kp, 64));
+            GGD_TRY(make_tmap_bf16(&p.b_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 64));
+            GGD_TRY(make_tmap_bf16(&p.b_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 64));
+            GemmArgs &a = p.args;
+            a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
+            a.I = ly.Kp; a.J = ly.Np; a.kblocks = h->Mp / 64;
+            a.o32 = h->G + ly.w_off; a.ld32 = ly.Np;
+            p.splits = 1;
+        }
+    }
+    return GGD_OK;
+}
+
+static int ensure_chunk(ggd_handle *h, size_t frames)
+{
+    if (frames <= h->cap) return GGD_OK;
+    free_chunk(h);
+    size_t cap = frames + h->Mp;   // slack so that a padded last tile never leaves the allocation
+    const int D = h->units[h->L - 1];
+    GGD_CUDA(cudaMalloc(&h->c_in, cap * h->units[0] * sizeof(float)));
+    GGD_CUDA(cudaMalloc(&h->c_targ, cap * D * sizeof(float)));
+    GGD_CUDA(cudaMalloc(&h->c_out, cap * D * sizeof(float)));
+    GGD_CUDA(cudaMemset(h->c_in, 0, cap * h->units[0] * sizeof(float)));
+    GGD_CUDA(cudaMemset(h->c_targ, 0, cap * D * sizeof(float)));
+    if (h->tensor) {
+        GGD_CUDA(cudaMalloc(&h->c_hi, cap * h->upad[0] * sizeof(bf16)));
+        GGD_CUDA(cudaMalloc(&h->c_lo, cap * h->upad[0] * sizeof(bf16)));
+        GGD_CUDA(cudaMemset(h->c_hi, 0, cap * h->upad[0] * sizeof(bf16)));
+        GGD_CUDA(cudaMemset(h->c_lo, 0, cap * h->upad[0] * sizeof(bf16)));
+    }
+    h->trace_cap = cap / h->M + 2;
+    GGD_CUDA(cudaMalloc(&h->trace, h->trace_cap * sizeof(double)));
+    h->cap = cap;
+    if (h->tensor) GGD_TRY(build_plans(h));
+    return GGD_OK;
+}
+
+// ---- one training step (forward, loss gradient, backward, update); stream-ordered, no host sync ----
+static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches)
+{
+    const int L = h->L;
+    if (h->tensor) {
+        for (int l = 1; l < L; l++) { GGD_TRY(launch_gemm_tc(h->fwd[l], s)); (*launches)++; }
+    } else {
+        launch_simt_gather_in(h->ctl, h->M, h->units[0], h->y32[0], h->upad[0], s); (*launches)++;
+        for (int l = 1; l < L; l++) {
+            const LayerInfo &ly = h->lay[l];
+            launch_simt_gemm(h->y32[l - 1], ly.Kp, 1, h->P + ly.w_off, 1, ly.Np, h->x32[l], ly.Np, h->M, ly.cur, ly.prev, s);
+            launch_simt_bias_act(h->x32[l], ly.Np, h->P + ly.b_off, (l == L - 1) ? h->out32 : h->y32[l], h->M, ly.cur, l == L - 1, s);
+            (*launches) += 2;
+        }
+    }
+    return GGD_OK;
+}
+
+static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *launches)
+{
+    const int L = h->L;
+    const LayerInfo &top = h->lay[L - 1];
+    GGD_TRY(enqueue_forward(h, s, launches));
+    // ---- fused loss gradient (BP_GPU.cu:408-424)
+    LossArgs la;
+    memset(&la, 0, sizeof la);
+    la.ctl = h->ctl; la.out = h->out32; la.ldo = top.Np; la.M = h->M; la.Mg = h->Mg; la.D = top.cur;
+    la.beta = h->cfg.shapefactor; la.ml = (h->cfg.MLflag == 1);
+    la.dx32 = h->tensor ? nullptr : h->dx32[L - 1];
+    la.dx_hi = h->tensor ? h->dx_hi[L - 1] : nullptr; la.dx_lo = h->tensor ? h->dx_lo[L - 1] : nullptr;
+    la.ldx = top.Np; la.alpha = h->alpha; la.colsum = h->colsum; la.trace = h->trace;
+    if (h->has_comm && la.ml) {
+        la.mode = 1; launch_loss(la, s);
+        GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, top.cur, ncclFloat, ncclSum, h->comm, s));
+        la.mode = 2; launch_loss(la, s);
+        (*launches) += 3;
+    } else {
+        la.mode = 0; launch_loss(la, s); (*launches)++;
+    }
+    // ---- backward (BP_GPU.cu:371-438); every GEMM of the step sees the pre-update weights
+    for (int l = L - 1; l > 0; l--) {
+        const LayerInfo &ly = h->lay[l];
+        if (h->tensor) {
+            if (l != 1) { GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
+            GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++;
+            launch_bias_grad(nullptr, h->dx_hi[l], h->dx_lo[l], ly.Np, h->M, ly.cur, h->G + ly.b_off, s); (*launches)++;
+        } else {
+            if (l != L - 1) { launch_simt_dsigmoid(h->y32[l], h->dy32[l], h->dx32[l], ly.Np, h->M, ly.cur, s); (*launches)++; }
+            if (l != 1) {
+                launch_simt_gemm(h->dx32[l], ly.Np, 1, h->P + ly.w_off, ly.Np, 1, h->dy32[l - 1], ly.Kp, h->M, ly.prev, ly.cur, s);
+                (*launches)++;
+            }
+            launch_simt_gemm(h->y32[l - 1], 1, ly.Kp, h->dx32[l], 1, ly.Np, h->G + ly.w_off, ly.Np, ly.prev, ly.cur, h->M, s);
+            launch_bias_grad(h->dx32[l], nullptr, nullptr, ly.Np, h->M, ly.cur, h->G + ly.b_off, s);
+            (*launches) += 2;
+        }
+    }
+    if (h->has_comm) {
+        // frame-sharded data parallelism: sum the weight and bias gradients of all ranks
+        GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena, ncclFloat, ncclSum, h->comm, s));
+        (*launches)++;
+    }
+    if (apply_update) {
+        UpdArgs ua;
+        memset(&ua, 0, sizeof ua);
+        for (int l = 1; l < L; l++) {
+            const LayerInfo &ly = h->lay[l];
+            ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
+            ua.seg[ua.nseg++] = {(long long)ly.b_off, (long long)ly.Np, 0.0f, 0};   // no decay on biases (BP_GPU.cu:435)
+        }
+        ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
+        ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
+        launch_update(ua, h->sm_count, s); (*launches)++;
+    }
+    launch_advance(h->ctl, s); (*launches)++;
+    GGD_CUDA(cudaGetLastError());
+    return GGD_OK;
+}
+
+static int capture_graph(ggd_handle *h, int steps, cudaGraphExec_t *out)
+{
+    cudaGraph_t g;
+    int launches = 0;
+    GGD_CUDA(cudaStreamBeginCapture(h->s_main, cudaStreamCaptureModeThreadLocal));
+    int rc = GGD_OK;
+    for (int i = 0; i < steps && rc == GGD_OK; i++) rc = enqueue_step(h, h->s_main, true, &launches);
+    cudaError_t e = cudaStreamEndCapture(h->s_main, &g);
+    if (rc != GGD_OK) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
+    GGD_CUDA(e);
+    GGD_CUDA(cudaGraphInstantiate(out, g, 0));
+    cudaGraphDestroy(g);
+    h->launches_per_step = launches / steps;
+    return GGD_OK;
+}
+
+static int set_ctl(ggd_handle *h, const float *d_in, const float *d_targ)
+{
+    StepCtl c;
+    c.bunch_idx = 0; c.pad = 0; c.in32 = d_in; c.targ = d_targ;
+    GGD_CUDA(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->s_main));
+    return GGD_OK;
+}
+
+static int upload(ggd_handle *h, const float *src, float *dst, size_t bytes)
+{
+    // pin the caller's (reused) buffer once so that the copy is a real DMA (the reference hands us pageable memory)
+    if ((h->cfg.flags & GGD_FLAG_PIN_HOST) && bytes >= (1u << 20) && h->pinned.find(src) == h->pinned.end()) {
+        cudaError_t e = cudaHostRegister(const_cast<float *>(src), bytes, cudaHostRegisterDefault);
+        if (e == cudaSuccess) h->pinned[src] = bytes;
+        else { cudaGetLastError(); h->pinned[src] = 0; }
+    }
+    GGD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_main));
+    return GGD_OK;
+}
+
+static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ)
+{
+    const int nb = n_frames / h->M;   // trailing partial bunch dropped (BP_GPU.cu:173-180)
+    h->stats.steps = nb; h->stats.launches = 0;
+    h->losses.assign(nb, 0.0f);
+    if (nb == 0) { h->stats.device_ms = 0; return GGD_OK; }
+    GGD_TRY(set_ctl(h, d_in, d_targ));
+    GGD_CUDA(cudaMemsetAsync(h->trace, 0, h->trace_cap * sizeof(double), h->s_main));
+    GGD_CUDA(cudaEventRecord(h->ev1, h->s_main));
+    if (h->tensor) { launch_split_rows(d_in, nb * h->M, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main); h->stats.launches++; }
+    if (h->cfg.flags & GGD_FLAG_NO_GRAPH) {
+        int launches = 0;
+        for (int b = 0; b < nb; b++) GGD_TRY(enqueue_step(h, h->s_main, true, &launches));
+        h->stats.launches += launches;
+    } else {
+        if (!h->g1) {
+            GGD_TRY(capture_graph(h, 1, &h->g1));
+            h->gN_steps = 16;
+            GGD_TRY(capture_graph(h, h->gN_steps, &h->gN));
+        }
+        int b = 0;
+        for (; b + h->gN_steps <= nb; b += h->gN_steps) GGD_CUDA(cudaGraphLaunch(h->gN, h->s_main));
+        for (; b < nb; b++) GGD_CUDA(cudaGraphLaunch(h->g1, h->s_main));
+        h->stats.launches += (long long)nb * h->launches_per_step;
+    }
+    GGD_CUDA(cudaEventRecord(h->ev2, h->s_main));
+    std::vector<double> tr(nb);
+    GGD_CUDA(cudaMemcpyAsync(tr.data(), h->trace, nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    float ms = 0;
+    GGD_CUDA(cudaEventElapsedTime(&ms, h->ev1, h->ev2));
+    h->stats.device_ms = ms;
+    for (int b = 0; b < nb; b++) h->losses[b] = (float)tr[b];
+    h->stats.d2h_bytes = nb * sizeof(double);
+    return GGD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *ggd_last_error(void) { return g_err; }
+const char *ggd_version(void) { return "ggd_b200 0.1 (sm_100a; tcgen05 bf16x3)"; }
+
+int ggd_create(const ggd_config *cfg, const float *const *weights, const float *const *bias, ggd_handle **out)
+{
+    if (!cfg || !weights || !bias || !out) { set_error("ggd_create: null argument"); return GGD_EINVAL; }
+    if (cfg->numlayers < 2 || cfg->numlayers > GGD_MAXLAYER) { set_error("numlayers %d out of range", cfg->numlayers); return GGD_EINVAL; }
+    if (cfg->bunchsize < 1) { set_error("bunchsize must be >= 1"); return GGD_EINVAL; }
+    if (cfg->dropoutflag == 1) { set_error("dropoutflag=1 is outside the named path and not supported"); return GGD_EUNSUPPORTED; }
+    if (!(cfg->shapefactor > 0)) { set_error("shapefactor must be > 0"); return GGD_EINVAL; }
+    for (int i = 0; i < cfg->numlayers; i++)
+        if (cfg->layersizes[i] < 1) { set_error("layersizes[%d] invalid", i); return GGD_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device: libggd_b200 has no CPU fallback"); return GGD_ECUDA; }
+    if (cfg->gpu < 0 || cfg->gpu >= ndev) { set_error("GPU Num %d Not In Range 0-%d", cfg->gpu, ndev - 1); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(cfg->gpu));
+    cudaDeviceProp prop;
+    GGD_CUDA(cudaGetDeviceProperties(&prop, cfg->gpu));
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", cfg->gpu, prop.major, prop.minor); return GGD_ECUDA; }
+
+    ggd_handle *h = new ggd_handle();
+    h->cfg = *cfg;
+    h->L = cfg->numlayers; h->M = cfg->bunchsize; h->Mp = round_up(h->M, 128);
+    h->sm_count = prop.multiProcessorCount;
+    h->tensor = (cfg->precision == GGD_PREC_BF16X3);
+    const int world = cfg->world_size > 1 ? cfg->world_size : 1;
+    h->Mg = h->M * world;
+    size_t off = 0;
+    for (int i = 0; i < h->L; i++) { h->units[i] = cfg->layersizes[i]; h->upad[i] = round_up(h->units[i], 64); }
+    for (int l = 1; l < h->L; l++) {
+        LayerInfo &ly = h->lay[l];
+        ly.prev = h->units[l - 1]; ly.cur = h->units[l]; ly.Kp = h->upad[l - 1]; ly.Np = h->upad[l];
+        ly.w_off = off; off += (size_t)ly.Kp * ly.Np;
+        ly.b_off = off; off += ly.Np;
+    }
+    h->arena = off;
+    auto fail = [&](int rc) { ggd_destroy(h); return rc; };
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s -> %s", #expr, cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? GGD_ENOMEM : GGD_ECUDA); } } while (0)
+    CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev2));
+    CK(cudaMalloc(&h->P, off * sizeof(float))); CK(cudaMalloc(&h->Dl, off * sizeof(float))); CK(cudaMalloc(&h->G, off * sizeof(float)));
+    CK(cudaMalloc(&h->Phi, off * sizeof(bf16))); CK(cudaMalloc(&h->Plo, off * sizeof(bf16)));
+    CK(cudaMemset(h->P, 0, off * sizeof(float))); CK(cudaMemset(h->Dl, 0, off * sizeof(float))); CK(cudaMemset(h->G, 0, off * sizeof(float)));
+    CK(cudaMemset(h->Phi, 0, off * sizeof(bf16))); CK(cudaMemset(h->Plo, 0, off * sizeof(bf16)));
+    for (int l = 0; l < h->L; l++) {
+        const size_t n = (size_t)h->Mp * h->upad[l];
+        if (h->tensor) {
+            if (l >= 1) {
+                CK(cudaMalloc(&h->act_hi[l], n * sizeof(bf16))); CK(cudaMalloc(&h->act_lo[l], n * sizeof(bf16)));
+                CK(cudaMalloc(&h->dx_hi[l], n * sizeof(bf16))); CK(cudaMalloc(&h->dx_lo[l], n * sizeof(bf16)));
+                CK(cudaMemset(h->act_hi[l], 0, n * sizeof(bf16))); CK(cudaMemset(h->act_lo[l], 0, n * sizeof(bf16)));
+                CK(cudaMemset(h->dx_hi[l], 0, n * sizeof(bf16))); CK(cudaMemset(h->dx_lo[l], 0, n * sizeof(bf16)));
+            }
+        } else {
+            CK(cudaMalloc(&h->x32[l], n * sizeof(float))); CK(cudaMalloc(&h->y32[l], n * sizeof(float)));
+            CK(cudaMalloc(&h->dy32[l], n * sizeof(float))); CK(cudaMalloc(&h->dx32[l], n * sizeof(float)));
+            CK(cudaMemset(h->x32[l], 0, n * sizeof(float))); CK(cudaMemset(h->y32[l], 0, n * sizeof(float)));
+            CK(cudaMemset(h->dy32[l], 0, n * sizeof(float))); CK(cudaMemset(h->dx32[l], 0, n * sizeof(float)));
+        }
+    }
+    const int D = h->units[h->L - 1];
+    CK(cudaMalloc(&h->out32, (size_t)h->Mp * h->upad[h->L - 1] * sizeof(float)));
+    CK(cudaMemset(h->out32, 0, (size_t)h->Mp * h->upad[h->L - 1] * sizeof(float)));
+    CK(cudaMalloc(&h->alpha, D * sizeof(float))); CK(cudaMalloc(&h->colsum, D * sizeof(float)));
+    CK(cudaMemset(h->alpha, 0, D * sizeof(float))); CK(cudaMemset(h->colsum, 0, D * sizeof(float)));
+    CK(cudaMalloc(&h->ctl, sizeof(StepCtl))); CK(cudaMemset(h->ctl, 0, sizeof(StepCtl)));
+    // weights in: reference order (out + in*cur) -> padded pitch Np; then build the bf16 shadows with a zero-gradient-free pass
+    for (int l = 1; l < h->L; l++) {
+        const LayerInfo &ly = h->lay[l];
+        if (!weights[l] || !bias[l]) { set_error("weights[%d]/bias[%d] is null", l, l); return fail(GGD_EINVAL); }
+        CK(cudaMemcpy2D(h->P + ly.w_off, ly.Np * sizeof(float), weights[l], ly.cur * sizeof(float), ly.cur * sizeof(float), ly.prev, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->P + ly.b_off, bias[l], ly.cur * sizeof(float), cudaMemcpyHostToDevice));
+        launch_split_rows(h->P + ly.w_off, ly.Kp, ly.Np, h->Phi + ly.w_off, h->Plo + ly.w_off, ly.Np, 0);
+    }
+    CK(cudaDeviceSynchronize());
+    if (h->tensor) { int rc = gemm_tc_init(); if (rc != GGD_OK) return fail(rc); }
+    if (world > 1) {
+        if (!cfg->nccl_unique_id) { set_error("world_size > 1 needs nccl_unique_id"); return fail(GGD_EINVAL); }
+        ncclUniqueId id;
+        memcpy(&id, cfg->nccl_unique_id, sizeof id);
+        ncclResult_t r = ncclCommInitRank(&h->comm, world, id, cfg->rank);
+        if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", ncclGetErrorString(r)); return fail(GGD_ENCCL); }
+        h->has_comm = true;
+    }
+#undef CK
+    *out = h;
+    return GGD_OK;
+}
+
+int ggd_destroy(ggd_handle *h)
+{
+    if (!h) return GGD_OK;
+    cudaSetDevice(h->cfg.gpu);
+    if (h->s_main) cudaStreamSynchronize(h->s_main);
+    free_chunk(h);
+    for (auto &kv : h->pinned) if (kv.second) cudaHostUnregister(const_cast<void *>(kv.first));
+    if (h->has_comm) ncclCommDestroy(h->comm);
+    cudaFree(h->P); cudaFree(h->Dl); cudaFree(h->G); cudaFree(h->Phi); cudaFree(h->Plo);
+    for (int l = 0; l < GGD_MAXLAYER; l++) {
+        cudaFree(h->act_hi[l]); cudaFree(h->act_lo[l]); cudaFree(h->dx_hi[l]); cudaFree(h->dx_lo[l]);
+        cudaFree(h->x32[l]); cudaFree(h->y32[l]); cudaFree(h->dy32[l]); cudaFree(h->dx32[l]);
+    }
+    cudaFree(h->out32); cudaFree(h->alpha); cudaFree(h->colsum); cudaFree(h->ctl);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->s_main) cudaStreamDestroy(h->s_main);
+    delete h;
+    return GGD_OK;
+}
+
+int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ)
+{
+    if (!h || !in || !targ || n_frames < 0) { set_error("ggd_train: bad argument"); return GGD_EINVAL; }
+    if (n_frames > GGD_MAXCACHEFRAME) { set_error("n_frames %d exceeds MAXCACHEFRAME %d", n_frames, GGD_MAXCACHEFRAME); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    const int D = h->units[h->L - 1];
+    const size_t bi = (size_t)n_frames * h->units[0] * sizeof(float), bt = (size_t)n_frames * D * sizeof(float);
+    GGD_CUDA(cudaEventRecord(h->ev0, h->s_main));
+    GGD_TRY(upload(h, in, h->c_in, bi));
+    GGD_TRY(upload(h, targ, h->c_targ, bt));
+    GGD_TRY(run_chunk(h, n_frames, h->c_in, h->c_targ));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.h2d_ms = ms; h->stats.h2d_bytes = bi + bt;
+    return GGD_OK;
+}
+
+int ggd_train_device(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ)
+{
+    if (!h || !d_in || !d_targ || n_frames < 0) { set_error("ggd_train_device: bad argument"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    h->stats.h2d_ms = 0; h->stats.h2d_bytes = 0;
+    return run_chunk(h, n_frames, d_in, d_targ);
+}
+
+// forward-only over n frames in bunches of M (a partial last bunch IS processed: BP_GPU.cu:203-218)
+static int forward_chunk(ggd_handle *h, int n_frames, const float *in)
+{
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    const int D = h->units[h->L - 1], ldo = h->upad[h->L - 1];
+    GGD_TRY(upload(h, in, h->c_in, (size_t)n_frames * h->units[0] * sizeof(float)));
+    GGD_TRY(set_ctl(h, h->c_in, h->c_targ));
+    const int nb = ceil_div(n_frames, h->M);
+    if (h->tensor) launch_split_rows(h->c_in, n_frames, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main);
+    int launches = 0;
+    for (int b = 0; b < nb; b++) {
+        const int f = (n_frames - b * h->M < h->M) ? n_frames - b * h->M : h->M;
+        GGD_TRY(enqueue_forward(h, h->s_main, &launches));
+        GGD_CUDA(cudaMemcpy2DAsync(h->c_out + (size_t)b * h->M * D, D * sizeof(float), h->out32, ldo * sizeof(float), D * sizeof(float), f,
+                                   cudaMemcpyDeviceToDevice, h->s_main));
+        launch_advance(h->ctl, h->s_main);
+    }
+    h->h_out.resize((size_t)n_frames * D);
+    GGD_CUDA(cudaMemcpyAsync(h->h_out.data(), h->c_out, (size_t)n_frames * D * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    return GGD_OK;
+}
+
+int ggd_forward(ggd_handle *h, int n_frames, const float *in, float *out)
+{
+    if (!h || !in || !out || n_frames < 0) { set_error("ggd_forward: bad argument"); return GGD_EINVAL; }
+    GGD_TRY(forward_chunk(h, n_frames, in));
+    memcpy(out, h->h_out.data(), h->h_out.size() * sizeof(float));
+    return GGD_OK;
+}
+
+// The three CV metrics accumulate on the host in float, frame-major order, exactly like the reference.
+int ggd_cv_sqerr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result)
+{
+    if (!h || !in || !targ || !result) { set_error("ggd_cv_sqerr: bad argument"); return GGD_EINVAL; }
+    GGD_TRY(forward_chunk(h, n_frames, in));
+    const size_t n = (size_t)n_frames * h->units[h->L - 1];
+    const float *o = h->h_out.data();
+    float s = 0.0f;
+    for (size_t i = 0; i < n; i++) s = s + (o[i] - targ[i]) * (o[i] - targ[i]);   // BP_GPU.cu:211
+    *result = s;
+    return GGD_OK;
+}
+
+int ggd_cv_abserr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result)
+{
+    if (!h || !in || !targ || !result) { set_error("ggd_cv_abserr: bad argument"); return GGD_EINVAL; }
+    GGD_TRY(forward_chunk(h, n_frames, in));
+    const int D = h->units[h->L - 1];
+    const size_t n = (size_t)n_frames * D;
+    const float *o = h->h_out.data();
+    float s = 0.0f;
+    for (size_t i = 0; i < n; i++) s = s + fabsf(o[i] - targ[i]);                  // BP_GPU.cu:244
+    *result = s / D;                                                               // BP_GPU.cu:250
+    return GGD_OK;
+}
+
+static float gamma_ref(float x)   // BP_GPU::Gamma, BP_GPU.cu:593-640
+{
+    if (x > 2 && x <= 3) {
+        static const float c[11] = {0.0000677106f, -0.0003442342f, 0.0015397681f, -0.0024467480f, 0.0109736958f, -0.0002109075f,
+                                    0.0742379071f, 0.0815782188f,  0.4118402518f, 0.4227843370f,  1.0000000000f};
+        const double t = x - 2.0;
+        float temp = 0;
+        temp = temp + c[0] * pow(t, 10.0) + c[1] * pow(t, 9.0);
+        temp = temp + c[2] * pow(t, 8.0) + c[3] * pow(t, 7.0);
+        temp = temp + c[4] * pow(t, 6.0) + c[5] * pow(t, 5.0);
+        temp = temp + c[6] * pow(t, 4.0) + c[7] * pow(t, 3.0);
+        temp = temp + c[8] * pow(t, 2.0) + c[9] * t + c[10];
+        return temp;
+    }
+    if (x > 0 && x <= 1) return gamma_ref(x + 2) / (x * (x + 1));
+    if (x > 1 && x <= 2) return gamma_ref(x + 1) / x;
+    if (x > 3) {
+        int i = 1;
+        float temp = 1;
+        while (!((x - i) > 2 && (x - i) <= 3)) { temp = (x - i) * temp; i++; }
+        temp = temp * (x - i);
+        return temp * gamma_ref(x - i);
+    }
+    return 0;
+}
+
+int ggd_cv_loglik(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result)
+{
+    if (!h || !in || !targ || !result) { set_error("ggd_cv_loglik: bad argument"); return GGD_EINVAL; }
+    GGD_TRY(forward_chunk(h, n_frames, in));
+    const int D = h->units[h->L - 1];
+    std::vector<float> al(D);
+    GGD_CUDA(cudaMemcpy(al.data(), h->alpha, D * sizeof(float), cudaMemcpyDeviceToHost));
+    const float sf = h->cfg.shapefactor;
+    const float *o = h->h_out.data();
+    float d1 = n_frames * D * logf(sf / (2 * gamma_ref((float)(1.0 / sf))));
+    float d2 = 0, d3 = 0;
+    for (int u = 0; u < D; u++) d2 += logf(al[u]);
+    d2 = d2 * n_frames;
+    for (int f = 0; f < n_frames; f++)
+        for (int d = 0; d < D; d++) d3 += powf(fabsf(targ[(size_t)f * D + d] - o[(size_t)f * D + d]) / al[d], sf);
+    *result = d1 - d2 - d3;                                                        // BP_GPU.cu:287-301
+    return GGD_OK;
+}
+
+int ggd_get_weights(ggd_handle *h, float *const *weights, float *const *bias)
+{
+    if (!h || !weights || !bias) { set_error("ggd_get_weights: bad argument"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    for (int l = 1; l < h->L; l++) {
+        const LayerInfo &ly = h->lay[l];
+        GGD_CUDA(cudaMemcpy2D(weights[l], ly.cur * sizeof(float), h->P + ly.w_off, ly.Np * sizeof(float), ly.cur * sizeof(float), ly.prev, cudaMemcpyDeviceToHost));
+        GGD_CUDA(cudaMemcpy(bias[l], h->P + ly.b_off, ly.cur * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return GGD_OK;
+}
+
+int ggd_get_alpha(ggd_handle *h, float *alpha)
+{
+    if (!h || !alpha) { set_error("ggd_get_alpha: bad argument"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    GGD_CUDA(cudaMemcpy(alpha, h->alpha, h->units[h->L - 1] * sizeof(float), cudaMemcpyDeviceToHost));
+    return GGD_OK;
+}
+
+int ggd_get_losses(ggd_handle *h, float *losses, int max, int *n)
+{
+    if (!h || !n) { set_error("ggd_get_losses: bad argument"); return GGD_EINVAL; }
+    const int k = (int)h->losses.size() < max ? (int)h->losses.size() : max;
+    if (losses) memcpy(losses, h->losses.data(), k * sizeof(float));
+    *n = (int)h->losses.size();
+    return GGD_OK;
+}
+
+int ggd_get_stats(ggd_handle *h, ggd_stats *s)
+{
+    if (!h || !s) { set_error("ggd_get_stats: bad argument"); return GGD_EINVAL; }
+    *s = h->stats;
+    return GGD_OK;
+}
+
+int ggd_debug_step(ggd_handle *h, int n_frames, const float *in, const float *targ, int apply_update)
+{
+    if (!h || !in || !targ || n_frames != h->M) { set_error("ggd_debug_step: n_frames must equal bunchsize"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    const int D = h->units[h->L - 1];
+    GGD_CUDA(cudaMemcpyAsync(h->c_in, in, (size_t)n_frames * h->units[0] * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->c_targ, targ, (size_t)n_frames * D * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    GGD_TRY(set_ctl(h, h->c_in, h->c_targ));
+    GGD_CUDA(cudaMemsetAsync(h->trace, 0, h->trace_cap * sizeof(double), h->s_main));
+    if (h->tensor) launch_split_rows(h->c_in, n_frames, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main);
+    int launches = 0;
+    GGD_TRY(enqueue_step(h, h->s_main, apply_update != 0, &launches));
+    double tr = 0;
+    GGD_CUDA(cudaMemcpyAsync(&tr, h->trace, sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    h->losses.assign(1, (float)tr);
+    return GGD_OK;
+}
+
+static int read_pair(ggd_handle *h, const bf16 *hi, const bf16 *lo, int ld, int rows, int cols, float *dst)
+{
+    std::vector<uint16_t> a((size_t)rows * ld), b((size_t)rows * ld);
+    GGD_CUDA(cudaMemcpy(a.data(), hi, a.size() * 2, cudaMemcpyDeviceToHost));
+    GGD_CUDA(cudaMemcpy(b.data(), lo, b.size() * 2, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < cols; c++) {
+            uint32_t x = (uint32_t)a[(size_t)r * ld + c] << 16, y = (uint32_t)b[(size_t)r * ld + c] << 16;
+            float fx, fy;
+            memcpy(&fx, &x, 4); memcpy(&fy, &y, 4);
+            dst[(size_t)r * cols + c] = fx + fy;
+        }
+    return GGD_OK;
+}
+
+int ggd_debug_read(ggd_handle *h, int what, int layer, float *dst)
+{
+    if (!h || !dst) { set_error("ggd_debug_read: bad argument"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    const int L = h->L;
+    if (what == 0) {
+        const int D = h->units[L - 1];
+        GGD_CUDA(cudaMemcpy2D(dst, D * sizeof(float), h->out32, h->upad[L - 1] * sizeof(float), D * sizeof(float), h->M, cudaMemcpyDeviceToHost));
+        return GGD_OK;
+    }
+    if (layer < 1 || layer >= L) { set_error("ggd_debug_read: layer %d out of range", layer); return GGD_EINVAL; }
+    const LayerInfo &ly = h->lay[layer];
+    switch (what) {
+    case 1:
+        if (h->tensor) return read_pair(h, h->dx_hi[layer], h->dx_lo[layer], ly.Np, h->M, ly.cur, dst);
+        GGD_CUDA(cudaMemcpy2D(dst, ly.cur * sizeof(float), h->dx32[layer], ly.Np * sizeof(float), ly.cur * sizeof(float), h->M, cudaMemcpyDeviceToHost));
+        return GGD_OK;
+    case 2:
+        if (layer == L - 1) { set_error("layer %d is linear: read what=0", layer); return GGD_EINVAL; }
+        if (h->tensor) return read_pair(h, h->act_hi[layer], h->act_lo[layer], ly.Np, h->M, ly.cur, dst);
+        GGD_CUDA(cudaMemcpy2D(dst, ly.cur * sizeof(float), h->y32[layer], ly.Np * sizeof(float), ly.cur * sizeof(float), h->M, cudaMemcpyDeviceToHost));
+        return GGD_OK;
+    case 3:
+        GGD_CUDA(cudaMemcpy2D(dst, ly.cur * sizeof(float), h->G + ly.w_off, ly.Np * sizeof(float), ly.cur * sizeof(float), ly.prev, cudaMemcpyDeviceToHost));
+        return GGD_OK;
+    case 4:
+        GGD_CUDA(cudaMemcpy(dst, h->G + ly.b_off, ly.cur * sizeof(float), cudaMemcpyDeviceToHost));
+        return GGD_OK;
+    }
+    set_error("ggd_debug_read: unknown selector %d", what);
+    return GGD_EINVAL;
+}
+
+int ggd_nccl_unique_id(void *out128)
+{
+    if (!out128) { set_error("ggd_nccl_unique_id: null argument"); return GGD_EINVAL; }
+    ncclUniqueId id;
+    GGD_NCCL(ncclGetUniqueId(&id));
+    memcpy(out128, &id, sizeof id);
+    return GGD_OK;
+}
+
+int ggd_debug_gemm(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, const float *A, const float *B, float *D)
+{
+    if (!A || !B || !D || I < 1 || J < 1 || R < 1) { set_error("ggd_debug_gemm: bad argument"); return GGD_EINVAL; }
+    GGD_TRY(gemm_tc_init());
+    const int Ip = round_up(I, 128), Jp = round_up(J, bn), Rp = round_up(R, 64);
+    const int Ic = round_up(I, 64), Jc = round_up(J, 64);
+    // operand shapes in memory: K-major [rows_p][Rp]; MN-major [Rp][rows rounded to 64]
+    const int a_rows = a_mn ? R : I, a_cols = a_mn ? I : R, a_ld = a_mn ? Ic : Rp, a_rp = a_mn ? Rp : Ip;
+    const int b_rows = b_mn ? R : J, b_cols = b_mn ? J : R, b_ld = b_mn ? Jc : Rp, b_rp = b_mn ? Rp : Jp;
+    float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+    bf16 *ah = nullptr, *al = nullptr, *bh = nullptr, *bl = nullptr;
+    int rc = GGD_OK;
+    auto cleanup = [&]() { cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(ah); cudaFree(al); cudaFree(bh); cudaFree(bl); };
+#define DG(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s -> %s", #expr, cudaGetErrorString(_e)); cleanup(); return GGD_ECUDA; } } while (0)
+    DG(cudaMalloc(&dA, (size_t)a_rows * a_cols * 4)); DG(cudaMalloc(&dB, (size_t)b_rows * b_cols * 4));
+    DG(cudaMalloc(&dD, (size_t)Ip * Jp * 4));
+    DG(cudaMalloc(&ah, (size_t)a_rp * a_ld * 2)); DG(cudaMalloc(&al, (size_t)a_rp * a_ld * 2));
+    DG(cudaMalloc(&bh, (size_t)b_rp * b_ld * 2)); DG(cudaMalloc(&bl, (size_t)b_rp * b_ld * 2));
+    DG(cudaMemset(ah, 0, (size_t)a_rp * a_ld * 2)); DG(cudaMemset(al, 0, (size_t)a_rp * a_ld * 2));
+    DG(cudaMemset(bh, 0, (size_t)b_rp * b_ld * 2)); DG(cudaMemset(bl, 0, (size_t)b_rp * b_ld * 2));
+    DG(cudaMemset(dD, 0xFF, (size_t)Ip * Jp * 4));
+    DG(cudaMemcpy(dA, A, (size_t)a_rows * a_cols * 4, cudaMemcpyHostToDevice));
+    DG(cudaMemcpy(dB, B, (size_t)b_rows * b_cols * 4, cudaMemcpyHostToDevice));
+    launch_split_rows(dA, a_rows, a_cols, ah, al, a_ld, 0);
+    launch_split_rows(dB, b_rows, b_cols, bh, bl, b_ld, 0);
+    GemmPlan p;
+    memset(&p, 0, sizeof p);
+    p.bn = bn; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = EPI_STORE_F32; p.splits = splits;
+    p.tiles_i = Ip / 128; p.tiles_j = Jp / bn;
+    rc = make_tmap_bf16(&p.a_hi, ah, a_rp, a_ld, a_ld, a_mn ? 64 : 128);
+    if (!rc) rc = make_tmap_bf16(&p.a_lo, al, a_rp, a_ld, a_ld, a_mn ? 64 : 128);
+    if (!rc) rc = make_tmap_bf16(&p.b_hi, bh, b_rp, b_ld, b_ld, b_mn ? 64 : bn);
+    if (!rc) rc = make_tmap_bf16(&p.b_lo, bl, b_rp, b_ld, b_ld, b_mn ? 64 : bn);
+    p.args.I = Ip; p.args.J = Jp; p.args.kblocks = Rp / 64; p.args.o32 = dD; p.args.ld32 = Jp;
+    if (!rc) rc = launch_gemm_tc(p, 0);
+    if (rc) { cleanup(); return rc; }
+    DG(cudaDeviceSynchronize());
+    DG(cudaMemcpy2D(D, (size_t)J * 4, dD, (size_t)Jp * 4, (size_t)J * 4, I, cudaMemcpyDeviceToHost));
+#undef DG
+    cleanup();
+    return GGD_OK;
+}
+
+}  // extern "C"

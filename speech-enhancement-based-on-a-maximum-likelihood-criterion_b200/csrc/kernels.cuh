@@ -1,0 +1,73 @@
+// kernels.cuh -- launch wrappers of the HBM-bound kernels of the training step
+// (input split, fused loss gradient, bias gradient, fused momentum-SGD update) and of the
+// fp32 CUDA-core validation GEMM.
+#pragma once
+#include "common.cuh"
+
+namespace ggd {
+
+typedef __nv_bfloat16 bf16;
+
+// Device-side step control block: read by every kernel of a step so that one captured CUDA graph
+// can be replayed for every bunch of a chunk (the bunch index advances on the device).
+struct StepCtl {
+    int bunch_idx;        // index of the current bunch inside the chunk
+    int pad;
+    const float *in32;    // chunk input, fp32 [frames][units0]   (reference layout)
+    const float *targ;    // chunk targets, fp32 [frames][D]
+};
+
+// fp32 [rows][cols] -> bf16 hi / lo [rows][ld] (columns >= cols are zeroed)
+void launch_split_rows(const float *src, int rows, int cols, bf16 *hi, bf16 *lo, int ld, cudaStream_t s);
+
+struct LossArgs {
+    const StepCtl *ctl;
+    const float *out;   // [M][ldo] network output of this bunch (fp32)
+    int ldo;
+    int M;              // frames of this bunch on this rank
+    int Mg;             // frames of the GLOBAL minibatch (== M on one GPU)
+    int D;              // output units
+    float beta;         // shapefactor
+    int ml;             // MLflag == 1
+    float *dx32;        // top-layer dE/dx, fp32 [M][ldx] (validation path) or NULL
+    bf16 *dx_hi, *dx_lo;  // top-layer dE/dx as bf16 hi/lo [M][ldx] or NULL
+    int ldx;
+    float *alpha;       // [D] GGD scale factors (kept for CrossValid2)
+    float *colsum;      // [D] sum_m |e|^beta  (partial in mode 1, global in mode 2)
+    double *trace;      // per-bunch loss trace, indexed by ctl->bunch_idx (may be NULL)
+    int mode;           // 0 = fused single pass-pair, 1 = column sums only, 2 = gradient from `colsum`
+};
+void launch_loss(const LossArgs &a, cudaStream_t s);
+
+// bias gradient: dst[n] = sum_{m<M} dedx[m][n]   (kernAccSumrow, DevFunc.cu:267-285)
+void launch_bias_grad(const float *dx32, const bf16 *dx_hi, const bf16 *dx_lo, int ld, int M, int N, float *dst, cudaStream_t s);
+
+struct UpdSeg {
+    long long off;   // element offset in the parameter arena (multiple of 4)
+    long long n;     // elements (multiple of 4)
+    float wc;        // weight cost (0 for biases)
+    int shadow;      // write bf16 hi/lo shadows
+};
+struct UpdArgs {
+    UpdSeg seg[2 * 10];
+    int nseg;
+    float *P, *Dl;       // parameters, momentum
+    const float *G;      // gradients (same arena layout)
+    bf16 *Phi, *Plo;     // bf16 split shadows of P (weights only)
+    float mom, lr, Mg;
+};
+// kernUpdatedelta + kernAccSum fused (DevFunc.cu:490-507, 427-443)
+void launch_update(const UpdArgs &a, int sm_count, cudaStream_t s);
+
+void launch_advance(StepCtl *ctl, cudaStream_t s);
+
+// fp32 validation GEMM: C[i][j] = sum_r A[i*sAi + r*sAr] * B[j*sBj + r*sBr]
+void launch_simt_gemm(const float *A, long sAi, long sAr, const float *B, long sBj, long sBr, float *C, long ldc,
+                      int I, int J, int R, cudaStream_t s);
+// x[m][n] + bias[n] -> sigmoid -> y  (or plain copy to y when linear)
+void launch_simt_bias_act(const float *x, int ld, const float *bias, float *y, int M, int N, int linear, cudaStream_t s);
+void launch_simt_dsigmoid(const float *y, const float *dedy, float *dedx, int ld, int M, int N, cudaStream_t s);
+// A-operand view of the current bunch of the fp32 chunk input (validation path)
+void launch_simt_gather_in(const StepCtl *ctl, int M, int K, float *dst, int ld, cudaStream_t s);
+
+}  // namespace ggd

@@ -1,0 +1,379 @@
+// lps.cu -- B200 LPS front end (include/lps_b200.h).
+//
+// One warp per frame.  The frame's 512 windowed samples live in shared memory; the warp executes the
+// reference's in-place split-radix real FFT (FEfunc.c:146-293) as a precomputed butterfly SCHEDULE:
+// the host walks the reference's loop nest once and records, stage by stage, every butterfly with its
+// indices and twiddles.  Butterflies of one stage touch disjoint elements, so the 32 lanes execute
+// them in parallel and only a __syncwarp() separates stages.  Every butterfly performs the reference's
+// float operations in the reference's order with explicit round-to-nearest intrinsics (no FMA
+// contraction), which makes the spectrum bit-identical to the reference; the floored natural log is
+// taken in double like the reference ((float)log((double)P), Wav2LogSpec_be.c:475-479).
+//
+// Loads: frame n covers samples [256n, 256n+512) (coalesced 64-byte warp loads, each sample is read by
+// the two frames that overlap it and hits L1/L2 the second time).  Stores: 257 consecutive floats per
+// frame, optionally byte-swapped for the HTK writer or z-scored for the trainer.
+#include "../../include/lps_b200.h"
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+thread_local char g_lps_err[512] = "";
+void lps_err(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_lps_err, sizeof g_lps_err, fmt, ap);
+    va_end(ap);
+}
+#define LPS_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            lps_err("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));  \
+            return -2;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+constexpr int N = LPS_FRAME_LEN, LOGN = 9;
+constexpr int WARPS = 8;
+constexpr int MAX_OPS = 704, MAX_TW = 128, NSTAGE = 9;
+
+// butterfly kinds
+enum { OP_LEN2 = 0, OP_L0 = 1, OP_L8 = 2, OP_LTW = 3 };
+// op word: [0,2) kind  [2,12) base index i  [12,20) j  [20,28) twiddle slot
+static inline uint32_t mk_op(int kind, int i, int j, int tw) { return (uint32_t)kind | ((uint32_t)i << 2) | ((uint32_t)j << 12) | ((uint32_t)tw << 20); }
+
+struct Schedule {
+    uint32_t ops[MAX_OPS];
+    float4 tw[MAX_TW];       // cc1, ss1, cc3, ss3
+    float win[N / 2];
+    int stage_beg[NSTAGE + 1];
+    int stage_n4[NSTAGE];
+    float floor_fb;          // (float)exp(-50.0)
+};
+
+// Walks the loop nest of the reference rfft(x, 512, 9) and records the butterflies (FEfunc.c:183-292).
+void build_schedule(Schedule &S)
+{
+    int nops = 0, ntw = 0, st = 0;
+    S.stage_beg[0] = 0; S.stage_n4[0] = 0;
+    for (int is = 0, id = 4; is < N - 1; is = 2 * id - 2, id *= 4)          // length-two butterflies, :184-199
+        for (int i0 = is; i0 < N; i0 += id) S.ops[nops++] = mk_op(OP_LEN2, i0, 0, 0);
+    S.stage_beg[++st] = nops;
+    int n2 = 2;
+    for (int k = 1; k < LOGN; k++) {                                         // L-shaped butterflies, :202-292
+        n2 <<= 1;
+        const int n4 = n2 >> 2, n8 = n2 >> 3;
+        const float e = (float)((3.14159265358979323846 * 2) / n2);
+        S.stage_n4[st] = n4;
+        // ops are grouped by kind inside a stage so that neighbouring lanes run the same code
+        for (int is = 0, id = n2 << 1; is < N; is = 2 * id - n2, id *= 4)
+            for (int i = is; i <= N - 1; i += id) S.ops[nops++] = mk_op(OP_L0, i, 0, 0);
+        if (n4 != 1)
+            for (int is = 0, id = n2 << 1; is < N; is = 2 * id - n2, id *= 4)
+                for (int i = is; i <= N - 1; i += id) S.ops[nops++] = mk_op(OP_L8, i + n8, 0, 0);
+        for (int j = 1; j < n8; j++) {
+            const float a = j * e, a3 = 3 * a;
+            S.tw[ntw] = make_float4((float)cos(a), (float)sin(a), (float)cos(a3), (float)sin(a3));
+            for (int is = 0, id = n2 << 1; is < N; is = 2 * id - n2, id *= 4)
+                for (int i = is; i <= N - 1; i += id) S.ops[nops++] = mk_op(OP_LTW, i, j, ntw);
+            ntw++;
+        }
+        S.stage_beg[++st] = nops;
+    }
+    for (int i = 0; i < N / 2; i++) S.win[i] = (float)(0.54 - 0.46 * cos(6.28318530717958647692 * i / (N - 1)));   // FEfunc.c:80-87
+    S.floor_fb = (float)exp((double)-50.0);
+    if (nops > MAX_OPS || ntw > MAX_TW || st != NSTAGE) { fprintf(stderr, "lps schedule overflow %d %d %d\n", nops, ntw, st); abort(); }
+}
+
+struct LpsArgs {
+    const int16_t *pcm;
+    const long long *utt_sample_off;   // [n_utts + 1]
+    const long long *utt_frame_off;    // [n_utts + 1]
+    int n_utts;
+    long long total_frames;
+    float *out;
+    const float *mean, *dvar;
+    int flags;
+    const Schedule *sched;
+};
+
+__global__ void __launch_bounds__(WARPS * 32) lps_kernel(const LpsArgs a)
+{
+    __shared__ Schedule S;
+    __shared__ float xs[WARPS][N];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.sched);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&S);
+        for (int i = threadIdx.x; i < (int)(sizeof(Schedule) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *x = xs[warp];
+    const double sqrt2_d = 1.41421356237309504880;
+
+    for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.total_frames; f += (long long)gridDim.x * WARPS) {
+        // utterance of this frame: largest u with frame_off[u] <= f
+        int lo = 0, hi = a.n_utts;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.utt_frame_off[mid] <= f) lo = mid; else hi = mid;
+        }
+        const long long base = a.utt_sample_off[lo] + (f - a.utt_frame_off[lo]) * LPS_FRAME_SHIFT;
+        const int16_t *src = a.pcm + base;
+        // window and bit-reversed scatter (ReadWave fileio.c:268-282, Window FEfunc.c:106-118, rfft :157-181)
+#pragma unroll
+        for (int e = 0; e < N / 32; e++) {
+            const int p = e * 32 + lane;
+            const float w = S.win[p < N / 2 ? p : N - 1 - p];
+            x[__brev((unsigned)p) >> (32 - LOGN)] = __fmul_rn((float)__ldg(src + p), w);
+        }
+        __syncwarp();
+        // stage 0: length-two butterflies
+        for (int o = S.stage_beg[0] + lane; o < S.stage_beg[1]; o += 32) {
+            const int i0 = (S.ops[o] >> 2) & 1023;
+            const float a0 = x[i0], a1 = x[i0 + 1];
+            x[i0] = __fadd_rn(a0, a1);
+            x[i0 + 1] = __fsub_rn(a0, a1);
+        }
+        __syncwarp();
+        for (int st = 1; st < NSTAGE; st++) {
+            const int n4 = S.stage_n4[st];
+            for (int o = S.stage_beg[st] + lane; o < S.stage_beg[st + 1]; o += 32) {
+                const uint32_t op = S.ops[o];
+                const int kind = op & 3, i = (op >> 2) & 1023;
+                if (kind == OP_L0) {                       // FEfunc.c:217-224
+                    const int i1 = i, i3 = i + 2 * n4, i4 = i3 + n4;
+                    const float x1 = x[i1], x3 = x[i3], x4 = x[i4];
+                    const float t1 = __fadd_rn(x4, x3);
+                    x[i4] = __fsub_rn(x4, x3);
+                    x[i3] = __fsub_rn(x1, t1);
+                    x[i1] = __fadd_rn(x1, t1);
+                } else if (kind == OP_L8) {                // FEfunc.c:226-238 (division by sqrt(2) in double)
+                    const int i1 = i, i2 = i1 + n4, i3 = i2 + n4, i4 = i3 + n4;
+                    const float x1 = x[i1], x2 = x[i2], x3 = x[i3], x4 = x[i4];
+                    const float t1 = __double2float_rn(__ddiv_rn((double)__fadd_rn(x3, x4), sqrt2_d));
+                    const float t2 = __double2float_rn(__ddiv_rn((double)__fsub_rn(x3, x4), sqrt2_d));
+                    x[i4] = __fsub_rn(x2, t1);
+                    x[i3] = __fsub_rn(-x2, t1);
+                    x[i2] = __fsub_rn(x1, t2);
+                    x[i1] = __fadd_rn(x1, t2);
+                } else {                                   // FEfunc.c:257-287
+                    const int j = (op >> 12) & 255;
+                    const float4 tw = S.tw[(op >> 20) & 255];
+                    const float cc1 = tw.x, ss1 = tw.y, cc3 = tw.z, ss3 = tw.w;
+                    const int i1 = i + j, i2 = i1 + n4, i3 = i2 + n4, i4 = i3 + n4;
+                    const int i5 = i + n4 - j, i6 = i5 + n4, i7 = i6 + n4, i8 = i7 + n4;
+                    const float x1 = x[i1], x2 = x[i2], x3 = x[i3], x4 = x[i4], x5 = x[i5], x6 = x[i6], x7 = x[i7], x8 = x[i8];
+                    float t1 = __fadd_rn(__fmul_rn(x3, cc1), __fmul_rn(x7, ss1));
+                    float t2 = __fsub_rn(__fmul_rn(x7, cc1), __fmul_rn(x3, ss1));
+                    float t3 = __fadd_rn(__fmul_rn(x4, cc3), __fmul_rn(x8, ss3));
+                    float t4 = __fsub_rn(__fmul_rn(x8, cc3), __fmul_rn(x4, ss3));
+                    const float t5 = __fadd_rn(t1, t3), t6 = __fadd_rn(t2, t4);
+                    t3 = __fsub_rn(t1, t3);
+                    t4 = __fsub_rn(t2, t4);
+                    x[i8] = __fadd_rn(x6, t6);
+                    x[i3] = __fsub_rn(t6, x6);
+                    x[i4] = __fsub_rn(x2, t3);
+                    x[i7] = __fsub_rn(-x2, t3);
+                    x[i1] = __fadd_rn(x1, t5);
+                    x[i6] = __fsub_rn(x1, t5);
+                    x[i2] = __fadd_rn(x5, t4);
+                    x[i5] = __fsub_rn(x5, t4);
+                }
+            }
+            __syncwarp();
+        }
+        // power spectrum + floored natural log (Wav2LogSpec_be.c:469-479); output order Re(0..256), Im(255..1)
+        float *dst = a.out + f * LPS_BINS;
+        for (int k = lane; k <= N / 2; k += 32) {
+            const float re = x[k];
+            float p = __fmul_rn(re, re);
+            if (k != 0 && k != N / 2) {
+                const float im = x[N - k];
+                p = __fadd_rn(p, __fmul_rn(im, im));
+            }
+            float v = (p < S.floor_fb) ? -50.0f : __double2float_rn(log((double)p));
+            if (a.flags & LPS_FLAG_ZSCORE) v = __fmul_rn(__fsub_rn(v, a.mean[k]), a.dvar[k]);   // Interface.cc:763-764
+            if (a.flags & LPS_FLAG_BIG_ENDIAN) v = __uint_as_float(__byte_perm(__float_as_uint(v), 0, 0x0123));
+            dst[k] = v;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+struct lps_handle {
+    int gpu, sm_count;
+    Schedule *d_sched;
+    float *d_mean, *d_dvar;
+    bool has_norm;
+    cudaStream_t s;
+    cudaEvent_t e0, e1;
+    // staging (grown on demand)
+    int16_t *d_pcm; size_t pcm_cap;
+    float *d_out; size_t out_cap;
+    long long *d_off; size_t off_cap;
+    double last_ms;
+};
+
+extern "C" {
+
+const char *lps_last_error(void) { return g_lps_err; }
+
+long lps_nframes(long n_samples)
+{
+    if (n_samples < LPS_FRAME_LEN) return 0;
+    return (n_samples - (LPS_FRAME_LEN - LPS_FRAME_SHIFT)) / LPS_FRAME_SHIFT;
+}
+
+int lps_create(int gpu, lps_handle **out)
+{
+    if (!out) { lps_err("lps_create: null argument"); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); lps_err("no CUDA device: liblps has no CPU fallback"); return -2; }
+    if (gpu < 0 || gpu >= ndev) { lps_err("gpu %d out of range 0-%d", gpu, ndev - 1); return -1; }
+    LPS_CUDA(cudaSetDevice(gpu));
+    cudaDeviceProp prop;
+    LPS_CUDA(cudaGetDeviceProperties(&prop, gpu));
+    if (prop.major != 10) { lps_err("device %d is sm_%d%d; built for sm_100a only", gpu, prop.major, prop.minor); return -2; }
+    lps_handle *h = new lps_handle();
+    h->gpu = gpu; h->sm_count = prop.multiProcessorCount;
+    Schedule *S = new Schedule();
+    memset(S, 0, sizeof *S);
+    build_schedule(*S);
+    LPS_CUDA(cudaMalloc(&h->d_sched, sizeof(Schedule)));
+    LPS_CUDA(cudaMemcpy(h->d_sched, S, sizeof(Schedule), cudaMemcpyHostToDevice));
+    delete S;
+    LPS_CUDA(cudaMalloc(&h->d_mean, LPS_BINS * sizeof(float)));
+    LPS_CUDA(cudaMalloc(&h->d_dvar, LPS_BINS * sizeof(float)));
+    LPS_CUDA(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
+    LPS_CUDA(cudaEventCreate(&h->e0));
+    LPS_CUDA(cudaEventCreate(&h->e1));
+    *out = h;
+    return 0;
+}
+
+int lps_destroy(lps_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->gpu);
+    cudaFree(h->d_sched); cudaFree(h->d_mean); cudaFree(h->d_dvar); cudaFree(h->d_pcm); cudaFree(h->d_out); cudaFree(h->d_off);
+    cudaEventDestroy(h->e0); cudaEventDestroy(h->e1); cudaStreamDestroy(h->s);
+    delete h;
+    return 0;
+}
+
+int lps_set_norm(lps_handle *h, const float *mean, const float *dvar)
+{
+    if (!h || !mean || !dvar) { lps_err("lps_set_norm: null argument"); return -1; }
+    LPS_CUDA(cudaSetDevice(h->gpu));
+    LPS_CUDA(cudaMemcpy(h->d_mean, mean, LPS_BINS * sizeof(float), cudaMemcpyHostToDevice));
+    LPS_CUDA(cudaMemcpy(h->d_dvar, dvar, LPS_BINS * sizeof(float), cudaMemcpyHostToDevice));
+    h->has_norm = true;
+    return 0;
+}
+
+static int offsets(lps_handle *h, const long *utt_off, int n_utts, std::vector<long long> &tab, long long *total)
+{
+    tab.resize(2 * (size_t)(n_utts + 1));
+    long long fr = 0;
+    for (int u = 0; u <= n_utts; u++) {
+        tab[u] = utt_off[u];
+        tab[n_utts + 1 + u] = fr;
+        if (u < n_utts) {
+            if (utt_off[u + 1] < utt_off[u]) { lps_err("utterance offsets must be non-decreasing"); return -1; }
+            fr += lps_nframes(utt_off[u + 1] - utt_off[u]);
+        }
+    }
+    *total = fr;
+    if (tab.size() > h->off_cap) {
+        cudaFree(h->d_off);
+        LPS_CUDA(cudaMalloc(&h->d_off, tab.size() * sizeof(long long)));
+        h->off_cap = tab.size();
+    }
+    LPS_CUDA(cudaMemcpyAsync(h->d_off, tab.data(), tab.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s));
+    return 0;
+}
+
+static int run_kernel(lps_handle *h, const int16_t *d_pcm, int n_utts, long long total, float *d_out, int flags)
+{
+    if ((flags & LPS_FLAG_ZSCORE) && !h->has_norm) { lps_err("LPS_FLAG_ZSCORE needs lps_set_norm first"); return -1; }
+    if ((flags & LPS_FLAG_ZSCORE) && (flags & LPS_FLAG_BIG_ENDIAN)) { lps_err("ZSCORE and BIG_ENDIAN cannot be combined"); return -1; }
+    LPS_CUDA(cudaEventRecord(h->e0, h->s));
+    if (total > 0) {
+        LpsArgs a;
+        a.pcm = d_pcm; a.utt_sample_off = h->d_off; a.utt_frame_off = h->d_off + n_utts + 1; a.n_utts = n_utts;
+        a.total_frames = total; a.out = d_out; a.mean = h->d_mean; a.dvar = h->d_dvar; a.flags = flags; a.sched = h->d_sched;
+        long long blocks = (total + WARPS - 1) / WARPS;
+        const long long cap = (long long)h->sm_count * 6;   // persistent-style grid: 6 resident CTAs per SM
+        if (blocks > cap) blocks = cap;
+        lps_kernel<<<(int)blocks, WARPS * 32, 0, h->s>>>(a);
+        LPS_CUDA(cudaGetLastError());
+    }
+    LPS_CUDA(cudaEventRecord(h->e1, h->s));
+    return 0;
+}
+
+int lps_extract_batch_device(lps_handle *h, const int16_t *d_pcm, const long *utt_off, int n_utts, float *d_out, int flags, long *total_frames)
+{
+    if (!h || !utt_off || n_utts < 0 || (n_utts > 0 && (!d_pcm || !d_out))) { lps_err("lps_extract_batch_device: bad argument"); return -1; }
+    LPS_CUDA(cudaSetDevice(h->gpu));
+    std::vector<long long> tab;
+    long long total = 0;
+    int rc = offsets(h, utt_off, n_utts, tab, &total);
+    if (rc) return rc;
+    rc = run_kernel(h, d_pcm, n_utts, total, d_out, flags);
+    if (rc) return rc;
+    LPS_CUDA(cudaStreamSynchronize(h->s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->e0, h->e1);
+    h->last_ms = ms;
+    if (total_frames) *total_frames = (long)total;
+    return 0;
+}
+
+int lps_extract_batch(lps_handle *h, const int16_t *pcm, const long *utt_off, int n_utts, float *out, int flags, long *total_frames)
+{
+    if (!h || !utt_off || n_utts < 0 || (n_utts > 0 && (!pcm || !out))) { lps_err("lps_extract_batch: bad argument"); return -1; }
+    LPS_CUDA(cudaSetDevice(h->gpu));
+    std::vector<long long> tab;
+    long long total = 0;
+    int rc = offsets(h, utt_off, n_utts, tab, &total);
+    if (rc) return rc;
+    const size_t ns = (size_t)(utt_off[n_utts] - utt_off[0]);
+    // rebase offsets to the uploaded span
+    if (utt_off[0] != 0) {
+        for (int u = 0; u <= n_utts; u++) tab[u] -= utt_off[0];
+        LPS_CUDA(cudaMemcpyAsync(h->d_off, tab.data(), tab.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s));
+    }
+    if (ns + 16 > h->pcm_cap) { cudaFree(h->d_pcm); h->d_pcm = nullptr; LPS_CUDA(cudaMalloc(&h->d_pcm, (ns + 16) * sizeof(int16_t))); h->pcm_cap = ns + 16; }
+    const size_t no = (size_t)total * LPS_BINS;
+    if (no > h->out_cap) { cudaFree(h->d_out); h->d_out = nullptr; LPS_CUDA(cudaMalloc(&h->d_out, (no + 1) * sizeof(float))); h->out_cap = no + 1; }
+    LPS_CUDA(cudaMemcpyAsync(h->d_pcm, pcm + utt_off[0], ns * sizeof(int16_t), cudaMemcpyHostToDevice, h->s));
+    rc = run_kernel(h, h->d_pcm, n_utts, total, h->d_out, flags);
+    if (rc) return rc;
+    if (no) LPS_CUDA(cudaMemcpyAsync(out, h->d_out, no * sizeof(float), cudaMemcpyDeviceToHost, h->s));
+    LPS_CUDA(cudaStreamSynchronize(h->s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->e0, h->e1);
+    h->last_ms = ms;
+    if (total_frames) *total_frames = (long)total;
+    return 0;
+}
+
+int lps_extract(lps_handle *h, const int16_t *pcm, long n_samples, float *out, int flags)
+{
+    const long off[2] = {0, n_samples};
+    return lps_extract_batch(h, pcm, off, 1, out, flags, nullptr);
+}
+
+double lps_last_kernel_ms(lps_handle *h) { return h ? h->last_ms : 0.0; }
+
+}  // extern "C"

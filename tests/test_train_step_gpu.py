@@ -1,0 +1,120 @@
+"""One training step / a few steps of the CUDA path against the C oracle (GPU only).
+
+Tolerances are the north star's: outputs, gradients and alpha within 1e-3 relative (Frobenius) for the
+tensor-core path (bf16x3, fp32 accumulate: measured ~1e-5) and 2e-5 for the fp32 validation path."""
+import numpy as np
+import pytest
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(O, layersizes, M, seed, beta_w=2.0):
+    rng = np.random.RandomState(seed)
+    W, b = O.init_weights(layersizes, seed=seed, beta=beta_w)
+    b = [rng.uniform(-0.1, 0.1, x.size).astype(np.float32) for x in b]
+    x = rng.randn(M, layersizes[0]).astype(np.float32)
+    t = rng.randn(M, layersizes[-1]).astype(np.float32)
+    return W, b, x, t
+
+
+def run_both(pkg, O, layersizes, M, MLflag, beta, precision, nsteps=1, seed=3, lr=0.1, mom=0.9, wc=1e-5):
+    W, b, x, t = make_case(O, layersizes, M * nsteps, seed)
+    orc = O.OracleNet(layersizes, M, lr, mom, wc, beta, MLflag, W, b)
+    net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, lr, mom, wc, W, b, beta, MLflag, precision=precision)
+    return orc, net, x, t
+
+
+SMALL = [70, 96, 80, 33]
+
+
+@pytest.mark.parametrize("precision,tol", [(1, 2e-5), (0, 1e-3)])
+@pytest.mark.parametrize("MLflag,beta", [(1, 1.5), (1, 1.0), (0, 2.0), (0, 1.0), (1, 2.0)])
+@pytest.mark.parametrize("M", [128, 50])
+def test_single_step_tensors(pkg, oracle, precision, tol, MLflag, beta, M):
+    O = oracle
+    orc, net, x, t = run_both(pkg, O, SMALL, M, MLflag, beta, precision)
+    orc.train_bunch(x, t)
+    net.debug_step(x, t, apply_update=True)
+    L = len(SMALL)
+    assert rel_err(net.debug_read(0), orc.out(M)) < tol
+    if MLflag == 1:
+        assert rel_err(net.alpha(), orc.alpha()) < tol
+    for l in range(1, L):
+        assert rel_err(net.debug_read(1, l), orc.dedx(l, M)) < tol, "dedx layer %d" % l
+        assert rel_err(net.debug_read(3, l), orc.grad(l)) < tol, "grad layer %d" % l
+        if l < L - 1:
+            assert rel_err(net.debug_read(2, l), orc.y(l, M)) < tol, "y layer %d" % l
+    Wg, bg = net.returnWeights()
+    Wo, bo = orc.weights()
+    for l in range(L - 1):
+        assert rel_err(Wg[l], Wo[l]) < tol
+        assert rel_err(bg[l], bo[l]) < tol
+        # the UPDATE itself (not just the weights, which barely move in one step) must agree
+    assert abs(net.losses()[0] - orc.last_loss()) <= 1e-3 * abs(orc.last_loss())
+
+
+def test_zero_error_branch(pkg, oracle):
+    """e == 0 must give exactly zero gradient (DevFunc.cu:388-391, 479-482)"""
+    O = oracle
+    layersizes, M = [8, 6, 5], 128
+    W, b, x, t = make_case(O, layersizes, M, 11)
+    for MLflag, beta in ((1, 1.5), (0, 1.0)):
+        net = pkg.BP_GPU(0, 0, 3, layersizes, M, 0.1, 0.9, 0.0, W, b, beta, MLflag, precision=1)
+        out = net.forward(x)
+        t2 = t.copy()
+        t2[::3] = out[::3]          # exact hits
+        net.debug_step(x, t2, apply_update=False)
+        d = net.debug_read(1, 2)
+        assert np.all(d[::3] == 0.0)
+        assert np.all(d[1::3] != 0.0)
+
+
+@pytest.mark.parametrize("precision,tol", [(1, 5e-5), (0, 1e-3)])
+def test_multi_step_chunk(pkg, oracle, precision, tol):
+    """ggd_train over a chunk (graph replay, device-side bunch counter, tail bunch dropped)"""
+    O = oracle
+    layersizes, M, nb = SMALL, 128, 19
+    W, b, x, t = make_case(O, layersizes, M * nb + 37, 5)
+    orc = O.OracleNet(layersizes, M, 0.05, 0.9, 1e-5, 1.5, 1, W, b)
+    net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, 0.05, 0.9, 1e-5, W, b, 1.5, 1, precision=precision)
+    lo, al = orc.train(x, t)
+    net.train(x.shape[0], x, t)
+    lg = net.losses()
+    assert len(lg) == nb == len(lo)
+    assert np.max(np.abs(lg - lo) / np.abs(lo)) < 5e-3       # loss curve within 0.5 %
+    assert rel_err(net.alpha(), al[-1]) < tol
+    Wg, bg = net.returnWeights()
+    Wo, bo = orc.weights()
+    for l in range(len(layersizes) - 1):
+        assert rel_err(Wg[l], Wo[l]) < tol
+        assert rel_err(bg[l], bo[l]) < 5 * tol
+    # CV metrics, partial last bunch included
+    xc, tc = x[:300], t[:300]
+    for f in ("cv_sqerr", "cv_abserr", "cv_loglik"):
+        ref = getattr(orc, f)(xc, tc)
+        got = {"cv_sqerr": net.CrossValid, "cv_abserr": net.CrossValiddB, "cv_loglik": net.CrossValid2}[f](300, xc, tc)
+        assert abs(got - ref) <= 2e-3 * abs(ref), (f, got, ref)
+
+
+def test_named_shape_step(pkg, oracle):
+    """the named configuration: 1799-2048-2048-2048-257, bunch 128, MLflag=1, beta=1.5"""
+    O = oracle
+    layersizes, M = [1799, 2048, 2048, 2048, 257], 128
+    W, b, x, t = make_case(O, layersizes, 2 * M, 9)
+    orc = O.OracleNet(layersizes, M, 0.1, 0.9, 1e-5, 1.5, 1, W, b)
+    net = pkg.BP_GPU(0, 0, 5, layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1)
+    orc.train_bunch(x[:M], t[:M])
+    net.debug_step(x[:M], t[:M], apply_update=True)
+    assert rel_err(net.debug_read(0), orc.out(M)) < 1e-3
+    assert rel_err(net.alpha(), orc.alpha()) < 1e-3
+    for l in range(1, 5):
+        assert rel_err(net.debug_read(3, l), orc.grad(l)) < 1e-3, l
+    # second step sees the updated weights
+    orc.train_bunch(x[M:], t[M:])
+    net.debug_step(x[M:], t[M:], apply_update=True)
+    assert rel_err(net.debug_read(0), orc.out(M)) < 1e-3
+    Wg, _ = net.returnWeights()
+    Wo, _ = orc.weights()
+    for l in range(4):
+        assert rel_err(Wg[l], Wo[l]) < 1e-3
