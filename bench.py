@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the BPtrain_Sigmoid training step (frames/s, fwd+bwd+update, GGD-ML).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU-runnable path (C oracle)
+
+A "step" is one bunch: `bunch` frames through forward, GGD loss gradient, backward and momentum-SGD update
+(BP_GPU::train_bunch_single, BP_GPU.cu:308-440).  Workload at every N: the named network
+1799-2048-2048-2048-257, 128 frames per GPU per step (weak scaling: the global minibatch is 128*N and
+alpha / the gradients are allreduced), MLflag=1, shapefactor=1.5, synthetic N(0,1) frames.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (layersizes, MLflag, shapefactor, frames per GPU per step)
+    "ggd_ml_1799x2048x3_257_b128": ([1799, 2048, 2048, 2048, 257], 1, 1.5, 128),
+    "mmse_1799x2048x3_257_b128": ([1799, 2048, 2048, 2048, 257], 0, 2.0, 128),
+    "ggd_ml_2827x2048x3_257_g1024": ([2827, 2048, 2048, 2048, 257], 1, 1.5, None),   # config 4: global 1024 / N
+}
+LR, MOM, WC = 0.1, 0.9, 1e-5
+
+
+def flops_per_frame(ls):
+    P = sum(ls[i] * ls[i + 1] for i in range(len(ls) - 1))
+    P1 = ls[0] * ls[1]
+    return 2 * P + 2 * P + 2 * (P - P1)          # fwd + dW + dX
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_net_inputs(ls, seed=1):
+    from oracle import oracle as O
+    return O.init_weights(ls, seed=seed, beta=2.0)
+
+
+def run_reference(args, ls, ml, beta, bunch):
+    """The reference's own CPU-runnable implementation of the path = the plain-C oracle (there is no CPU trainer in
+    the reference; oracle/ggd_oracle.c restates BP_GPU::train_bunch_single), OpenMP over the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    W, b = make_net_inputs(ls)
+    rng = np.random.RandomState(1)
+    net = O.OracleNet(ls, bunch, LR, MOM, WC, beta, ml, W, b)
+    x = rng.randn(bunch, ls[0]).astype(np.float32)
+    t = rng.randn(bunch, ls[-1]).astype(np.float32)
+    for _ in range(max(1, min(args.warmup, 2))):
+        net.train_bunch(x, t)
+    t0 = time.time()
+    done = 0
+    budget = 90.0
+    while done < args.steps and (time.time() - t0) < budget:
+        net.train_bunch(x, t)
+        done += 1
+    dt = time.time() - t0
+    val = done * bunch / dt
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": "train_frames_per_sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "timed_steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "bunch": bunch, "layersizes": ls, "MLflag": ml, "shapefactor": beta},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d bunches of %d frames through oracle/ggd_oracle.c (OpenMP, %d threads)" % (done, bunch, cores)},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=800)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ggd_ml_1799x2048x3_257_b128", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    ls, ml, beta, bunch = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if bunch is None:
+        bunch = 1024 // max(world, 1)
+    if args.impl == "reference":
+        return run_reference(args, ls, ml, beta, bunch)
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_pkg
+    pkg = load_pkg()
+    from se_ml_b200.bp_gpu import nccl_unique_id
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        box = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, b = make_net_inputs(ls)
+    prec = 0 if args.precision == "bf16x3" else 1
+    net = pkg.BP_GPU(0, local_rank, len(ls), ls, bunch, LR, MOM, WC, W, b, beta, ml, precision=prec, world_size=world, rank=rank,
+                     nccl_unique_id=uid)
+    K, Wm = args.steps, max(args.warmup, 3)
+    nfr = K * bunch
+    g = torch.Generator(device=dev); g.manual_seed(1 + rank)
+    d_in = torch.randn(max(nfr, Wm * bunch), ls[0], device=dev, generator=g)        # synthetic frames, resident in HBM
+    d_tg = torch.randn(max(nfr, Wm * bunch), ls[-1], device=dev, generator=g)
+    # ---- warm-up (also captures the CUDA graphs)
+    net.train_device(Wm * bunch, d_in.data_ptr(), d_tg.data_ptr())
+    barrier()
+    # ---- timed region: K steps, inputs already resident; the input set (737 MB + weights) exceeds the 126 MB L2
+    sampler = ClockSampler(local_rank); sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    net.train_device(nfr, d_in.data_ptr(), d_tg.data_ptr())
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st = net.stats()
+    dev_ms = st["device_ms"]
+    launches = int(st["launches"])
+    tmax = torch.tensor([max(ms, dev_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    clocks = sampler.finish()
+    value = K * bunch * world / (ms * 1e-3)
+
+    # ---- e2e: the public call with HOST (pinned) buffers: H2D of the chunk + steps + D2H of the loss trace
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.randn(nfr, ls[0], generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+        h_tg = torch.randn(nfr, ls[-1], generator=torch.Generator().manual_seed(8 + rank)).pin_memory()
+        xin, xtg = h_in.numpy(), h_tg.numpy()
+        net.train(Wm * bunch, xin[:Wm * bunch], xtg[:Wm * bunch])
+        barrier()
+        t0 = time.perf_counter()
+        net.train(nfr, xin, xtg)
+        _ = net.losses()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        s2 = net.stats()
+        e2e = {"value": K * bunch * world / float(tt.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": int(s2["h2d_bytes"] // K), "d2h_bytes_per_step": int(max(s2["d2h_bytes"], 8 * K) // K),
+               "h2d_ms": s2["h2d_ms"], "device_ms": s2["device_ms"]}
+        del h_in, h_tg
+
+    # ---- per-kernel times (CUDA events around every launch, no graph) -> roofline of the dominant kernel
+    peaks = measured_peaks()
+    kt = net.profile_kernels(64 * bunch, d_in.data_ptr(), d_tg.data_ptr())
+    steps_p = kt["steps"]
+    per_step = {k: (kt[k]["ms"] / steps_p, kt[k]["launches"] // max(steps_p, 1)) for k in kt if isinstance(kt[k], dict)}
+    fpf = flops_per_frame(ls)
+    P = sum(ls[i] * ls[i + 1] for i in range(len(ls) - 1)); P1 = ls[0] * ls[1]
+    gemm_flops = {"fwd_gemm": 2 * P * bunch, "dw_gemm": 2 * P * bunch, "dx_gemm": 2 * (P - P1) * bunch}
+    kern = {}
+    for k, (msk, n) in per_step.items():
+        if n == 0:
+            continue
+        ent = {"ms_per_step": msk, "launches_per_step": n}
+        if k in gemm_flops:
+            ent["tflops"] = gemm_flops[k] / (msk * 1e-3) / 1e12
+            ent["frac_of_bf16_sustained"] = ent["tflops"] / peaks["bf16_sus"]
+        if k == "update":
+            ent["gbs"] = 20.0 * kt["param_elems"] / (msk * 1e-3) / 1e9     # read W, delta, g; write W, delta (+4 B shadows not counted)
+        if k == "loss":
+            ent["gbs"] = (3 * 4 * bunch * 257 + 1028) / (msk * 1e-3) / 1e9
+        kern[k] = ent
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    if dom in gemm_flops:
+        ach = kern[dom]["tflops"]
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_sus"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sus"],
+                "traffic": None, "peak_source": peaks["src"] + " bf16 sustained (bf16x3 issues 3 MMAs per algorithmic product)"}
+    else:
+        ach = kern[dom].get("gbs", 0.0)
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                "peak_source": peaks["src"]}
+
+    # ---- CPU baseline on rank 0 at N=1: the C oracle on a bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        orc = O.OracleNet(ls, bunch, LR, MOM, WC, beta, ml, W, b)
+        xs = d_in[:bunch].cpu().numpy(); ts = d_tg[:bunch].cpu().numpy()
+        orc.train_bunch(xs, ts)
+        t0 = time.time(); n = 0
+        while n < 8 and time.time() - t0 < 20.0:
+            orc.train_bunch(xs, ts); n += 1
+        dtc = time.time() - t0
+        cpu = {"value": n * bunch / dtc, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d bunches of %d frames through oracle/ggd_oracle.c (OpenMP)" % (n, bunch)}
+
+    if rank == 0:
+        line = {"metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16x3 (bf16 hi+lo operands, fp32 TMEM accumulate, fp32 master weights)" if prec == 0 else "f32",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "layersizes": ls, "MLflag": ml, "shapefactor": beta, "frames_per_gpu_per_step": bunch,
+                           "global_minibatch": bunch * world, "l2": "inputs (737 MB/chunk) and weight state (250 MB) exceed the 126 MB L2",
+                           "parallelism": "dp%d (frame-sharded; allreduce of sum|e|^beta and of the gradients)" % world},
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "kernels": kern, "flops_per_frame": fpf,
+                "tensor_frac_whole_step": (fpf * bunch * K / (ms * 1e-3) / 1e12) / peaks["bf16_sus"]}
+        print(json.dumps(line), flush=True)
+    net.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

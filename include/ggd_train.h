@@ -109,6 +109,19 @@ typedef struct ggd_stats {
 } ggd_stats;
 int ggd_get_stats(ggd_handle *h, ggd_stats *s);
 
+/* Per-kernel timing: runs n_frames / bunchsize training steps WITHOUT the graph, with a CUDA-event pair
+ * around every launch on the compute stream, and returns the summed milliseconds and launch counts per
+ * kernel class (this is what bench.py divides the algorithmic bytes / FLOPs by). */
+enum { GGD_KC_FWD = 0, GGD_KC_LOSS, GGD_KC_DX, GGD_KC_DW, GGD_KC_BIAS, GGD_KC_ALLREDUCE, GGD_KC_UPDATE, GGD_KC_ADVANCE,
+       GGD_KC_SPLIT, GGD_KC_COUNT };
+typedef struct ggd_kernel_times {
+    double ms[16];
+    long long launches[16];
+    long long steps;
+    long long param_elems;   /* elements of the (padded) parameter arena the update kernel streams */
+} ggd_kernel_times;
+int ggd_profile_kernels(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ, ggd_kernel_times *out);
+
 /* Parity hooks (tests only): run ONE bunch with or without applying the update, then read tensors.
  * what: 0 = out [M][D], 1 = dedx of layer l [M][units], 2 = y of layer l, 3 = weight gradient of
  * layer l (reference order out + in*cur), 4 = bias gradient of layer l. */

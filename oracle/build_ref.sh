@@ -48,6 +48,30 @@ void refif_writeweights(void *p) { ((Interface *)p)->Writeweights(); }
 }
 EOS
 /usr/bin/g++ -O1 -w -fPIC -shared -fpermissive -I"$CUDA/include" -o "$OUT/libref_interface.so" "$TMP/Interface.cc" "$TMP/shim.cc" -lpthread
+# 2b. the reference's device path (BP_GPU.cu + DevFunc.cu, cuBLAS/cuRAND) as a shared library with a C shim,
+#     so that tests and bench.py can drive the UNMODIFIED reference CUDA code on identical in-memory inputs.
+cat > "$TMP/shim_bp.cu" <<'EOS'
+#include <stdio.h>
+#include <stdlib.h>
+#include "BP_GPU.h"
+extern "C" {
+void *refbp_create(int seed, int gpu, int numlayers, int *layersizes, int bunchsize, float lrate, float momentum, float weightcost,
+                   float **weights, float **bias, float shapefactor, int MLflag) {
+  BP_GPU *o = new BP_GPU(seed, gpu, numlayers, layersizes, bunchsize, lrate, momentum, weightcost, weights, bias, shapefactor, MLflag, 0, 0.0f, 0.0f);
+  cudaDeviceSynchronize();
+  return o; }
+void refbp_train(void *p, int n, float *in, const float *targ) { ((BP_GPU *)p)->train(n, in, targ); cudaDeviceSynchronize(); }
+float refbp_cv(void *p, int which, int n, const float *in, const float *targ) {
+  BP_GPU *o = (BP_GPU *)p; float r = which == 0 ? o->CrossValid(n, in, targ) : which == 1 ? o->CrossValiddB(n, in, targ) : o->CrossValid2(n, in, targ);
+  return r; }
+void refbp_weights(void *p, float **weights, float **bias) { ((BP_GPU *)p)->returnWeights(weights, bias); cudaDeviceSynchronize(); }
+void refbp_destroy(void *p) { delete (BP_GPU *)p; }
+}
+EOS
+if command -v nvcc >/dev/null; then
+  nvcc -w -O2 -gencode arch=compute_100a,code=sm_100a -I"$CUDA/include" -Xcompiler -fPIC -Xcompiler -fpermissive -shared -cudart shared \
+    -o "$OUT/libref_bpgpu.so" "$TMP/shim_bp.cu" "$TMP/BP_GPU.cu" "$TMP/DevFunc.cu" -lcublas -lcurand || echo "reference device library did not build"
+fi
 # 3. the reference CUDA trainer for sm_100a (second baseline + strongest oracle; runs on the GPU box)
 if command -v nvcc >/dev/null; then
   nvcc -w -O2 -gencode arch=compute_100a,code=sm_100a -I"$CUDA/include" -Xcompiler -fpermissive \

@@ -30,6 +30,13 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 16), ("launches", C.c_longlong * 16), ("steps", C.c_longlong), ("param_elems", C.c_longlong)]
+
+
+KERNEL_CLASSES = ("fwd_gemm", "loss", "dx_gemm", "dw_gemm", "bias_grad", "allreduce", "update", "advance", "split")
+
+
 def library_path():
     return os.path.join(_HERE, "libggd_b200.so")
 
@@ -55,6 +62,7 @@ def load_library():
         L.ggd_get_alpha.argtypes = [C.c_void_p, PF]
         L.ggd_get_losses.argtypes = [C.c_void_p, PF, C.c_int, C.POINTER(C.c_int)]
         L.ggd_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.ggd_profile_kernels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(KernelTimes)]
         L.ggd_debug_step.argtypes = [C.c_void_p, C.c_int, PF, PF, C.c_int]
         L.ggd_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_int, PF]
         L.ggd_debug_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, PF, PF, PF]
@@ -162,6 +170,14 @@ class BP_GPU:
     # ---- additions (same handle) ---------------------------------------------------------------
     def train_device(self, n_frames, d_in_ptr, d_targ_ptr):
         self._ck(self.L.ggd_train_device(self.h, n_frames, C.c_void_p(d_in_ptr), C.c_void_p(d_targ_ptr)))
+
+    def profile_kernels(self, n_frames, d_in_ptr, d_targ_ptr):
+        kt = KernelTimes()
+        self._ck(self.L.ggd_profile_kernels(self.h, n_frames, C.c_void_p(d_in_ptr), C.c_void_p(d_targ_ptr), C.byref(kt)))
+        out = {"steps": kt.steps, "param_elems": kt.param_elems}
+        for i, k in enumerate(KERNEL_CLASSES):
+            out[k] = {"ms": kt.ms[i], "launches": kt.launches[i]}
+        return out
 
     def forward(self, in_):
         in_ = _f32(in_)

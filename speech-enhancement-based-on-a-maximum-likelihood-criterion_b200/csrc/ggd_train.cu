@@ -87,6 +87,24 @@ struct ggd_handle {
     std::vector<float> losses;
     std::vector<float> h_out;
     ggd_stats stats;
+    // optional per-kernel timing (ggd_profile_kernels): events around every launch, by kernel class
+    bool prof_on;
+    std::vector<cudaEvent_t> prof_ev;     // pairs
+    std::vector<int> prof_cls;
+};
+
+enum { KC_FWD = 0, KC_LOSS, KC_DX, KC_DW, KC_BIAS, KC_ALLREDUCE, KC_UPDATE, KC_ADVANCE, KC_SPLIT, KC_COUNT };
+
+struct ProfScope {
+    ggd_handle *h; cudaStream_t s;
+    ProfScope(ggd_handle *h_, int cls, cudaStream_t s_) : h(h_), s(s_) {
+        if (!h->prof_on) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        h->prof_ev.push_back(a); h->prof_ev.push_back(b); h->prof_cls.push_back(cls);
+        cudaEventRecord(a, s);
+    }
+    ~ProfScope() { if (h->prof_on) cudaEventRecord(h->prof_ev.back(), s); }
 };
 
 static void free_chunk(ggd_handle *h)
@@ -205,7 +223,7 @@ static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches)
 {
     const int L = h->L;
     if (h->tensor) {
-        for (int l = 1; l < L; l++) { GGD_TRY(launch_gemm_tc(h->fwd[l], s)); (*launches)++; }
+        for (int l = 1; l < L; l++) { ProfScope ps(h, KC_FWD, s); GGD_TRY(launch_gemm_tc(h->fwd[l], s)); (*launches)++; }
     } else {
         launch_simt_gather_in(h->ctl, h->M, h->units[0], h->y32[0], h->upad[0], s); (*launches)++;
         for (int l = 1; l < L; l++) {
@@ -232,20 +250,21 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     la.dx_hi = h->tensor ? h->dx_hi[L - 1] : nullptr; la.dx_lo = h->tensor ? h->dx_lo[L - 1] : nullptr;
     la.ldx = top.Np; la.alpha = h->alpha; la.colsum = h->colsum; la.trace = h->trace;
     if (h->has_comm && la.ml) {
-        la.mode = 1; launch_loss(la, s);
-        GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, top.cur, ncclFloat, ncclSum, h->comm, s));
-        la.mode = 2; launch_loss(la, s);
+        { ProfScope ps(h, KC_LOSS, s); la.mode = 1; launch_loss(la, s); }
+        { ProfScope ps(h, KC_ALLREDUCE, s); GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, top.cur, ncclFloat, ncclSum, h->comm, s)); }
+        { ProfScope ps(h, KC_LOSS, s); la.mode = 2; launch_loss(la, s); }
         (*launches) += 3;
     } else {
+        ProfScope ps(h, KC_LOSS, s);
         la.mode = 0; launch_loss(la, s); (*launches)++;
     }
     // ---- backward (BP_GPU.cu:371-438); every GEMM of the step sees the pre-update weights
     for (int l = L - 1; l > 0; l--) {
         const LayerInfo &ly = h->lay[l];
         if (h->tensor) {
-            if (l != 1) { GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
-            GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++;
-            launch_bias_grad(nullptr, h->dx_hi[l], h->dx_lo[l], ly.Np, h->M, ly.cur, h->G + ly.b_off, s); (*launches)++;
+            if (l != 1) { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
+            { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
+            { ProfScope ps(h, KC_BIAS, s); launch_bias_grad(nullptr, h->dx_hi[l], h->dx_lo[l], ly.Np, h->M, ly.cur, h->G + ly.b_off, s); (*launches)++; }
         } else {
             if (l != L - 1) { launch_simt_dsigmoid(h->y32[l], h->dy32[l], h->dx32[l], ly.Np, h->M, ly.cur, s); (*launches)++; }
             if (l != 1) {
@@ -259,6 +278,7 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     }
     if (h->has_comm) {
         // frame-sharded data parallelism: sum the weight and bias gradients of all ranks
+        ProfScope ps(h, KC_ALLREDUCE, s);
         GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena, ncclFloat, ncclSum, h->comm, s));
         (*launches)++;
     }
@@ -272,9 +292,10 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         }
         ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
         ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
+        ProfScope ps(h, KC_UPDATE, s);
         launch_update(ua, h->sm_count, s); (*launches)++;
     }
-    launch_advance(h->ctl, s); (*launches)++;
+    { ProfScope ps(h, KC_ADVANCE, s); launch_advance(h->ctl, s); (*launches)++; }
     GGD_CUDA(cudaGetLastError());
     return GGD_OK;
 }
@@ -701,6 +722,35 @@ int ggd_debug_read(ggd_handle *h, int what, int layer, float *dst)
     }
     set_error("ggd_debug_read: unknown selector %d", what);
     return GGD_EINVAL;
+}
+
+int ggd_profile_kernels(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ, ggd_kernel_times *out)
+{
+    if (!h || !d_in || !d_targ || !out) { set_error("ggd_profile_kernels: bad argument"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    const int nb = n_frames / h->M;
+    memset(out, 0, sizeof *out);
+    if (nb == 0) return GGD_OK;
+    GGD_TRY(set_ctl(h, d_in, d_targ));
+    GGD_CUDA(cudaMemsetAsync(h->trace, 0, h->trace_cap * sizeof(double), h->s_main));
+    h->prof_on = true;
+    int rc = GGD_OK, launches = 0;
+    if (h->tensor) { ProfScope ps(h, KC_SPLIT, h->s_main); launch_split_rows(d_in, nb * h->M, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main); }
+    for (int b = 0; b < nb && rc == GGD_OK; b++) rc = enqueue_step(h, h->s_main, true, &launches);
+    h->prof_on = false;
+    cudaStreamSynchronize(h->s_main);
+    for (size_t i = 0; i < h->prof_cls.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]);
+        out->ms[h->prof_cls[i]] += ms;
+        out->launches[h->prof_cls[i]] += 1;
+    }
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    h->prof_ev.clear(); h->prof_cls.clear();
+    out->steps = nb;
+    out->param_elems = (long long)h->arena;
+    return rc;
 }
 
 int ggd_nccl_unique_id(void *out128)

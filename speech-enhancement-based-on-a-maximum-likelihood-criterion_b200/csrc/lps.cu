@@ -79,7 +79,8 @@ void build_schedule(Schedule &S)
                 for (int i = is; i <= N - 1; i += id) S.ops[nops++] = mk_op(OP_L8, i + n8, 0, 0);
         for (int j = 1; j < n8; j++) {
             const float a = j * e, a3 = 3 * a;
-            S.tw[ntw] = make_float4((float)cos(a), (float)sin(a), (float)cos(a3), (float)sin(a3));
+            // the reference is C: cos(float) promotes to double (in C++ the float overload would be picked)
+            S.tw[ntw] = make_float4((float)cos((double)a), (float)sin((double)a), (float)cos((double)a3), (float)sin((double)a3));
             for (int is = 0, id = n2 << 1; is < N; is = 2 * id - n2, id *= 4)
                 for (int i = is; i <= N - 1; i += id) S.ops[nops++] = mk_op(OP_LTW, i, j, ntw);
             ntw++;

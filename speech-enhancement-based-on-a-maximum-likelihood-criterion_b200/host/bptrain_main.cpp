@@ -1,0 +1,116 @@
+// BPtrain_Sigmoid drop-in: the process finetune.pl launches once per epoch (finetune.pl:50-76).
+// Same flags, same input / output files, same log lines as the reference's BPtrain.cc:55-146; the device
+// work goes through the C ABI of libggd_b200 (include/ggd_train.h).  A loader thread prefetches the next
+// chunk while the GPU trains on the current one (the reference's pthread double buffer, BPtrain.cc:15-54).
+#include "../../include/ggd_train.h"
+#include "interface.h"
+#include <condition_variable>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <thread>
+
+using namespace bphost;
+
+int main(int argc, char **argv)
+{
+    const time_t t0 = time(nullptr);
+    printf("--------activation functin is sigmoid--------\n");
+    Host H;
+    if (!H.init(argc, argv)) return 1;
+    Params &p = H.p;
+    ggd_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.numlayers = p.numlayers;
+    for (int i = 0; i < p.numlayers; i++) cfg.layersizes[i] = p.layersizes[i];
+    cfg.bunchsize = p.bunchsize; cfg.lrate = p.lrate; cfg.momentum = p.momentum; cfg.weightcost = p.weightcost;
+    cfg.shapefactor = p.shapefactor; cfg.MLflag = p.MLflag; cfg.dropoutflag = p.dropoutflag;
+    cfg.visible_omit = p.visible_omit; cfg.hid_omit = p.hid_omit; cfg.gpu = p.gpu_used; cfg.seed = p.init_randem_seed;
+    cfg.precision = p.precision; cfg.world_size = 1; cfg.flags = GGD_FLAG_PIN_HOST | (p.no_graph ? GGD_FLAG_NO_GRAPH : 0);
+    const float *Wp[GGD_MAXLAYER] = {nullptr}, *bp[GGD_MAXLAYER] = {nullptr};
+    for (int l = 1; l < p.numlayers; l++) { Wp[l] = H.W[l].data(); bp[l] = H.b[l].data(); }
+    ggd_handle *net = nullptr;
+    if (ggd_create(&cfg, Wp, bp, &net) != GGD_OK) { H.logf("%s\n", ggd_last_error()); printf("%s\n", ggd_last_error()); return 1; }
+    printf("Created net with %d layers, bunchsize %d.\n", p.numlayers, p.bunchsize);
+    if (!H.pfile_info()) return 1;
+
+    // ---- train
+    if (!H.chunk_info(p.train_sent_range, false)) return 1;
+    std::vector<int> order(H.total_chunks);
+    for (int i = 0; i < H.total_chunks; i++) order[i] = i;
+    H.shuffle(order);
+    // double buffer; the buffers are allocated once at full chunk size so that the library can pin them
+    std::vector<float> in[2], tg[2];
+    for (int k = 0; k < 2; k++) { in[k].reserve((size_t)p.traincache * p.layersizes[0]); tg[k].reserve((size_t)p.traincache * p.layersizes[p.numlayers - 1]); }
+    int samples[2] = {0, 0};
+    std::mutex mu;
+    std::condition_variable cv;
+    int filled = 0, consumed = 0;   // chunks produced / released
+    bool load_failed = false;
+    std::thread loader([&] {
+        for (int i = 0; i < H.total_chunks; i++) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return i - consumed < 2; });
+            }
+            const int n = H.read_chunk(order[i], false, in[i & 1], tg[i & 1]);
+            std::lock_guard<std::mutex> lk(mu);
+            samples[i & 1] = n;
+            if (n < 0) load_failed = true;
+            filled = i + 1;
+            cv.notify_all();
+            if (n < 0) return;
+        }
+    });
+    int rc = 0;
+    for (int i = 0; i < H.total_chunks && rc == 0; i++) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return filled > i || load_failed; });
+            if (load_failed) { rc = 1; break; }
+        }
+        H.logf("Starting chunk %d of %d containing %d samples.\n", i + 1, H.total_chunks, samples[i & 1]);
+        if (samples[i & 1] % p.bunchsize) printf("this bunch has only %d samples and is ignored.\n", samples[i & 1] % p.bunchsize);
+        if (ggd_train(net, samples[i & 1], in[i & 1].data(), tg[i & 1].data()) != GGD_OK) { H.logf("%s\n", ggd_last_error()); rc = 1; }
+        std::lock_guard<std::mutex> lk(mu);
+        consumed = i + 1;
+        cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu); consumed = H.total_chunks + 2; cv.notify_all(); }
+    loader.join();
+    if (rc) return rc;
+    H.logf("Total cost time: %.1f s.\n", (double)(time(nullptr) - t0));
+
+    printf("begin to write weights\n");
+    float *Wo[GGD_MAXLAYER] = {nullptr}, *bo[GGD_MAXLAYER] = {nullptr};
+    for (int l = 1; l < p.numlayers; l++) { Wo[l] = H.W[l].data(); bo[l] = H.b[l].data(); }
+    if (ggd_get_weights(net, Wo, bo) != GGD_OK) { H.logf("%s\n", ggd_last_error()); return 1; }
+    H.write_weights();
+    printf("finish to write weights\n\n");
+
+    // ---- cross validation (BPtrain.cc:114-139)
+    printf("begin to CV\n");
+    H.logf("Starting CV.\n");
+    if (!H.chunk_info(p.cv_sent_range, true)) return 1;
+    float squared_err = 0.f, db_err = 0.f, likelihood = 0.f;
+    for (int i = 0; i < H.cv_total_chunks; i++) {
+        const int n = H.read_chunk(i, true, in[0], tg[0]);
+        if (n < 0) return 1;
+        printf("cur_chunk_samples=%d\n", n);
+        float r = 0;
+        if (ggd_cv_sqerr(net, n, in[0].data(), tg[0].data(), &r) != GGD_OK) { H.logf("%s\n", ggd_last_error()); return 1; }
+        squared_err += r;
+        if (ggd_cv_abserr(net, n, in[0].data(), tg[0].data(), &r) != GGD_OK) { H.logf("%s\n", ggd_last_error()); return 1; }
+        db_err += r;
+        if (p.MLflag == 1) {
+            if (ggd_cv_loglik(net, n, in[0].data(), tg[0].data(), &r) != GGD_OK) { H.logf("%s\n", ggd_last_error()); return 1; }
+            likelihood += r;
+        }
+    }
+    H.logf("CV over. squared error: %f\n", squared_err / H.cv_total_samples);
+    H.logf("CV over. square root squared error: %f\n", db_err / H.cv_total_samples);
+    if (p.MLflag == 1) H.logf("CV2 over. CV log likelihood: %f\n", likelihood / H.cv_total_samples);
+    printf("all finish!\n");
+    ggd_destroy(net);
+    return 0;
+}

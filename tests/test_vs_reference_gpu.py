@@ -1,0 +1,141 @@
+"""Parity against the UNMODIFIED reference CUDA code (oracle/_ref/, built from /root/reference by
+oracle/build_ref.sh) running on the same B200: the strongest pin of both the C oracle and the CUDA path.
+Skipped where oracle/_ref was not built."""
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+from conftest import rel_err, GOLDEN, PKG_DIR, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(O, ls, n, seed):
+    rng = np.random.RandomState(seed)
+    W, b = O.init_weights(ls, seed=seed)
+    b = [rng.uniform(-0.1, 0.1, x.size).astype(np.float32) for x in b]
+    return W, b, rng.randn(n, ls[0]).astype(np.float32), rng.randn(n, ls[-1]).astype(np.float32)
+
+
+@pytest.mark.parametrize("MLflag,beta", [(1, 1.5), (1, 1.0), (0, 2.0)])
+def test_chunk_vs_reference_cuda(pkg, oracle, MLflag, beta):
+    from oracle import refcuda
+    if not refcuda.available("libref_bpgpu.so"):
+        pytest.skip("oracle/_ref/libref_bpgpu.so not built")
+    O = oracle
+    ls, M, nb = [7 * 33, 160, 96, 33], 128, 12
+    W, b, x, t = _case(O, ls, nb * M + 11, 21)
+    ref = refcuda.RefBPGPU(ls, M, 0.05, 0.9, 1e-5, beta, MLflag, W, b)
+    ref.train(x, t)
+    Wr, br = ref.weights()
+    xc, tc = x[:333], t[:333]
+    cv_ref = [ref.cv(k, xc, tc) for k in range(3 if MLflag == 1 else 2)]
+    ref.close()
+    orc = O.OracleNet(ls, M, 0.05, 0.9, 1e-5, beta, MLflag, W, b)
+    orc.train(x, t)
+    Wo, bo = orc.weights()
+    cv_orc = [orc.cv_sqerr(xc, tc), orc.cv_abserr(xc, tc)] + ([orc.cv_loglik(xc, tc)] if MLflag == 1 else [])
+    for precision, tol in ((1, 2e-4), (0, 1e-3)):
+        net = pkg.BP_GPU(0, 0, len(ls), ls, M, 0.05, 0.9, 1e-5, W, b, beta, MLflag, precision=precision)
+        net.train(x.shape[0], x, t)
+        Wg, bg = net.returnWeights()
+        cv_got = [net.CrossValid(333, xc, tc), net.CrossValiddB(333, xc, tc)] + ([net.CrossValid2(333, xc, tc)] if MLflag == 1 else [])
+        for l in range(len(ls) - 1):
+            assert rel_err(Wg[l], Wr[l]) < tol, ("W", l, precision)
+            assert rel_err(bg[l], br[l]) < 5 * tol, ("b", l, precision)
+        for g, r in zip(cv_got, cv_ref):
+            assert abs(g - r) <= 2e-3 * abs(r), (cv_got, cv_ref)
+        net.close()
+    # the oracle itself against the reference (this is what pins the oracle)
+    for l in range(len(ls) - 1):
+        assert rel_err(Wo[l], Wr[l]) < 2e-4
+        assert rel_err(bo[l], br[l]) < 1e-3
+    for o, r in zip(cv_orc, cv_ref):
+        assert abs(o - r) <= 1e-3 * abs(r)
+
+
+def _log_values(path):
+    txt = open(path).read()
+    vals = {}
+    for key, pat in (("sq", r"CV over\. squared error: ([-\d.eE+naninf]+)"), ("abs", r"square root squared error: ([-\d.eE+naninf]+)"),
+                     ("ll", r"CV log likelihood: ([-\d.eE+naninf]+)"), ("samples", r"Training sentences have (\d+) chunks, (\d+) samples"),
+                     ("cv_samples", r"CV sentences have (\d+) chunks, (\d+) samples")):
+        m = re.search(pat, txt)
+        if m:
+            vals[key] = float(m.group(len(m.groups())))
+    return vals
+
+
+@pytest.mark.parametrize("MLflag,beta", [(1, 1.5), (0, 2.0)])
+def test_cli_epoch_on_bundled_pfile(pkg, oracle, tmp_path, MLflag, beta):
+    """One finetune.pl epoch (same flags) on the bundled pfiles: this repository's BPtrain_Sigmoid vs the
+    reference's own binary; compares the written .wts and the CV lines of the log."""
+    from oracle import refcuda
+    O = oracle
+    mine = os.path.join(PKG_DIR, "host", "BPtrain_Sigmoid")
+    if not os.path.exists(mine):
+        pytest.skip("host/BPtrain_Sigmoid not built")
+    ls = [1799, 2048, 2048, 2048, 257]
+    W, b = O.init_weights(ls, seed=4)
+    init = str(tmp_path / "init.wts")
+    O.write_wts(init, ls, W, b)
+
+    def flags(tag):
+        return ["gpu_used=0", "numlayers=5", "layersizes=1799,2048,2048,2048,257", "bunchsize=128", "MLflag=%d" % MLflag,
+                "shapefactor=%g" % beta, "momentum=0.9", "weightcost=0.00001", "lrate=0.1", "fea_dim=257", "fea_context=7",
+                "traincache=102400", "init_randem_seed=27870775", "targ_offset=3", "initwts_file=" + init,
+                "norm_file=" + os.path.join(GOLDEN, "train_noisy.norm"), "fea_file=" + os.path.join(GOLDEN, "train_noisy.pfile"),
+                "targ_file=" + os.path.join(GOLDEN, "train_clean.pfile"), "outwts_file=" + str(tmp_path / (tag + ".wts")),
+                "log_file=" + str(tmp_path / (tag + ".log")), "train_sent_range=0-7", "cv_sent_range=8-9", "dropoutflag=0",
+                "visible_omit=0.1", "hid_omit=0.1"]
+    subprocess.run([mine] + flags("mine"), check=True, cwd=str(tmp_path), stdout=subprocess.DEVNULL)
+    vm = _log_values(str(tmp_path / "mine.log"))
+    assert vm["samples"] == 1443 and vm["cv_samples"] == 382
+    Wm, bm = O.read_wts(str(tmp_path / "mine.wts"), ls)
+    # oracle epoch through the numpy loader restatement
+    ld = O.PfileLoader(os.path.join(GOLDEN, "train_noisy.pfile"), os.path.join(GOLDEN, "train_clean.pfile"),
+                       os.path.join(GOLDEN, "train_noisy.norm"), 257, 7, 3, 102400, 27870775)
+    st, tot = ld.chunk_info(0, 7)
+    x, t = ld.read_chunk(st, tot, 7, 0)
+    orc = O.OracleNet(ls, 128, 0.1, 0.9, 1e-5, beta, MLflag, W, b)
+    orc.train(x, t)
+    Wo, bo = orc.weights()
+    cst, ctot = ld.chunk_info(8, 9)
+    xc, tc = ld.read_chunk(cst, ctot, 9, 0, shuffle=False)
+    for l in range(4):
+        assert rel_err(Wm[l], Wo[l]) < 1e-3, l
+    assert abs(vm["sq"] - orc.cv_sqerr(xc, tc) / ctot) <= 2e-3 * abs(vm["sq"])
+    assert abs(vm["abs"] - orc.cv_abserr(xc, tc) / ctot) <= 2e-3 * abs(vm["abs"])
+    if MLflag == 1:
+        assert abs(vm["ll"] - orc.cv_loglik(xc, tc) / ctot) <= 2e-3 * abs(vm["ll"])
+    if refcuda.available("BPtrain_ref"):
+        subprocess.run([os.path.join(refcuda.REF, "BPtrain_ref")] + flags("ref"), check=True, cwd=str(tmp_path), stdout=subprocess.DEVNULL)
+        vr = _log_values(str(tmp_path / "ref.log"))
+        Wr, br = O.read_wts(str(tmp_path / "ref.wts"), ls)
+        for l in range(4):
+            assert rel_err(Wm[l], Wr[l]) < 1e-3, ("mine vs reference binary", l)
+            assert rel_err(Wo[l], Wr[l]) < 1e-3, ("oracle vs reference binary", l)
+        for k in ("sq", "abs") + (("ll",) if MLflag == 1 else ()):
+            assert abs(vm[k] - vr[k]) <= 2e-3 * abs(vr[k]), (k, vm, vr)
+        # keep the reference's numbers next to ours for the record
+        print("reference log:", vr, "ours:", vm)
+
+
+def test_wav2lps_cli(pkg, oracle, tmp_path):
+    """Wav2LPS_be drop-in writes the reference's HTK file byte-for-byte (up to last-place log differences)."""
+    exe = os.path.join(PKG_DIR, "host", "Wav2LPS_be")
+    if not os.path.exists(exe):
+        pytest.skip("host/Wav2LPS_be not built")
+    name = "TEST_DR8_MPAM0_SX289"
+    pcm = oracle.read_wav_pcm16(os.path.join(GOLDEN, name + ".wav"))
+    raw, out = str(tmp_path / "x.raw"), str(tmp_path / "x.lps")
+    pcm.tofile(raw)
+    subprocess.run([exe, "-F", "RAW", "-fs", "16", raw, out], check=True, stderr=subprocess.DEVNULL)
+    a, b = open(out, "rb").read(), open(os.path.join(GOLDEN, name + ".lps"), "rb").read()
+    assert len(a) == len(b) and a[:12] == b[:12]
+    ha, fa = oracle.read_htk(out)
+    hb, fb = oracle.read_htk(os.path.join(GOLDEN, name + ".lps"))
+    assert ha == hb
+    assert np.mean(fa.view(np.uint32) != fb.view(np.uint32)) < 1e-3
+    assert np.all(np.abs(fa - fb) <= 1e-4 * np.maximum(np.abs(fb), 1.0))
