@@ -340,6 +340,46 @@ void ggd_oracle_train_bunch_sharded(ggd_oracle *o, int world, int Ms, const floa
     free(colsum); free(tot); free(outs); free(others);
 }
 
+/* ---- phase-wise entry points used by the multi-process (gloo, world_size 2) CPU tests: they mirror what each
+ * rank of the frame-sharded CUDA path does between its two collectives. ------------------------ */
+/* phase 1: forward on the local shard, local sum_m |e|^beta per output dimension */
+void ggd_oracle_dp_colsum(ggd_oracle *o, int Ms, int Mg, const float *in, const float *targ, float *colsum)
+{
+    const int D = o->layersizes[o->numlayers - 1];
+    forward(o, Ms, in, o->out);
+    const int ml = o->MLflag;
+    o->MLflag = 1;
+    loss_gradient(o, Ms, Mg, targ, NULL, colsum);
+    o->MLflag = ml;
+    (void)D;
+}
+/* phase 2: local gradients given the GLOBAL column sums (after allreduce); no update */
+void ggd_oracle_dp_backward(ggd_oracle *o, int Ms, int Mg, const float *in, const float *targ, const float *colsum_global, const float *colsum_local)
+{
+    const int D = o->layersizes[o->numlayers - 1];
+    float *others = zalloc(D);
+    for (int d = 0; d < D; d++) others[d] = colsum_global[d] - colsum_local[d];
+    loss_gradient(o, Ms, Mg, targ, o->MLflag == 1 ? others : NULL, NULL);
+    backward_update(o, Ms, Mg, in, NULL, NULL, 0);
+    free(others);
+}
+/* phase 3: momentum-SGD update from the (allreduced) gradients stored back into ydedx / sumdedx */
+void ggd_oracle_dp_update(ggd_oracle *o, int Mg)
+{
+    for (int l = o->numlayers - 1; l > 0; l--) {
+        const size_t nw = (size_t)o->layersizes[l] * o->layersizes[l - 1];
+        for (size_t i = 0; i < nw; i++) {
+            o->dW[l][i] = o->momentum * o->dW[l][i] - o->lrate * (o->ydedx[l][i] / Mg + o->weightcost * o->W[l][i]);
+            o->W[l][i] = o->dW[l][i] + 1.0f * o->W[l][i];
+        }
+        for (int u = 0; u < o->layersizes[l]; u++) {
+            o->db[l][u] = o->momentum * o->db[l][u] - o->lrate * (o->sumdedx[l][u] / Mg + 0.0f * o->b[l][u]);
+            o->b[l][u] = o->db[l][u] + 1.0f * o->b[l][u];
+        }
+    }
+}
+float *ggd_oracle_bias_grad(ggd_oracle *o, int l) { return o->sumdedx[l]; }
+
 /* cv forward for n frames in bunches (partial last bunch IS processed, BP_GPU.cu:203-218) */
 void ggd_oracle_forward(ggd_oracle *o, int n_frames, const float *in, float *out)
 {

@@ -51,6 +51,11 @@ def lib():
         for f in ("ggd_oracle_alpha", "ggd_oracle_out"):
             getattr(L, f).restype = PF
             getattr(L, f).argtypes = [C.c_void_p]
+        L.ggd_oracle_dp_colsum.argtypes = [C.c_void_p, C.c_int, C.c_int, PF, PF, PF]
+        L.ggd_oracle_dp_backward.argtypes = [C.c_void_p, C.c_int, C.c_int, PF, PF, PF, PF]
+        L.ggd_oracle_dp_update.argtypes = [C.c_void_p, C.c_int]
+        L.ggd_oracle_bias_grad.restype = PF
+        L.ggd_oracle_bias_grad.argtypes = [C.c_void_p, C.c_int]
         L.ggd_oracle_last_loss.restype = C.c_float
         L.ggd_oracle_last_loss.argtypes = [C.c_void_p]
         L.lps_oracle_nframes.restype = C.c_long
@@ -155,6 +160,28 @@ class OracleNet:
 
     def y(self, l, M):
         return self._arr(self.L.ggd_oracle_y(self.h, l), M * self.layersizes[l]).reshape(M, self.layersizes[l])
+
+    # --- frame-sharded data parallelism, one rank's view (used by the gloo tests)
+    def dp_colsum(self, Mg, x, t):
+        x = np.ascontiguousarray(x, np.float32); t = np.ascontiguousarray(t, np.float32)
+        cs = np.zeros(self.D, np.float32)
+        self.L.ggd_oracle_dp_colsum(self.h, x.shape[0], Mg, _fp(x), _fp(t), _fp(cs))
+        return cs
+
+    def dp_backward(self, Mg, x, t, colsum_global, colsum_local):
+        x = np.ascontiguousarray(x, np.float32); t = np.ascontiguousarray(t, np.float32)
+        g = np.ascontiguousarray(colsum_global, np.float32); l = np.ascontiguousarray(colsum_local, np.float32)
+        self.L.ggd_oracle_dp_backward(self.h, x.shape[0], Mg, _fp(x), _fp(t), _fp(g), _fp(l))
+
+    def grad_views(self):
+        """writable numpy views of the weight / bias gradient buffers (to allreduce in place)"""
+        n = len(self.layersizes)
+        gw = [np.ctypeslib.as_array(self.L.ggd_oracle_grad(self.h, l), shape=(self.layersizes[l] * self.layersizes[l - 1],)) for l in range(1, n)]
+        gb = [np.ctypeslib.as_array(self.L.ggd_oracle_bias_grad(self.h, l), shape=(self.layersizes[l],)) for l in range(1, n)]
+        return gw, gb
+
+    def dp_update(self, Mg):
+        self.L.ggd_oracle_dp_update(self.h, Mg)
 
     def last_loss(self):
         return float(self.L.ggd_oracle_last_loss(self.h))

@@ -131,7 +131,9 @@ bool Host::init(int argc, char **argv)
         W[l].assign((size_t)p.layersizes[l] * p.layersizes[l - 1], 0.f);
         b[l].assign(p.layersizes[l], 0.f);
     }
-    srand48(p.init_randem_seed);   // :411 -- one stream for chunk order and sample order
+    // :411 srand48(seed) -- one stream for chunk order and sample order.  The POSIX 48-bit LCG is restated here
+    // (X' = 0x5DEECE66D * X + 0xB mod 2^48, seed -> (seed << 16) | 0x330E) so that the loader owns its state.
+    rng_state = (((uint64_t)(uint32_t)p.init_randem_seed) << 16) | 0x330E;
     if (p.initwts_file.empty()) { logf("fatal_error, please set initial weights file\n"); return false; }   // :425-427
     FILE *fw = fopen(p.initwts_file.c_str(), "rb");
     if (!fw) { logf("can not open initial weights file: %s\n", p.initwts_file.c_str()); return false; }
@@ -237,7 +239,8 @@ void Host::shuffle(std::vector<int> &v)
 {
     const int n = (int)v.size();
     for (int i = 0; i < n - 1; i++) {
-        const int idx = (int)(lrand48() % (n - i));
+        rng_state = (0x5DEECE66DULL * rng_state + 0xBULL) & ((1ULL << 48) - 1);
+        const int idx = (int)((long)(rng_state >> 17) % (n - i));   // lrand48() % (len - i), :982
         std::swap(v[idx], v[n - 1 - i]);
     }
 }
@@ -315,3 +318,44 @@ bool Host::write_weights()
 }
 
 }  // namespace bphost
+
+// ---- plain-C view of the loader (used by the CPU tests and by bindings written in other languages) ----------
+extern "C" {
+void *bph_create(int argc, char **argv)
+{
+    bphost::Host *h = new bphost::Host();
+    if (!h->init(argc, argv) || !h->pfile_info()) { delete h; return nullptr; }
+    return h;
+}
+void bph_destroy(void *p) { delete (bphost::Host *)p; }
+int bph_numlayers(void *p) { return ((bphost::Host *)p)->p.numlayers; }
+int bph_chunk_info(void *p, const char *range, int cv, int *chunks, int *samples)
+{
+    bphost::Host *h = (bphost::Host *)p;
+    if (!h->chunk_info(range, cv != 0)) return -1;
+    *chunks = cv ? h->cv_total_chunks : h->total_chunks;
+    *samples = cv ? h->cv_total_samples : h->total_samples;
+    return 0;
+}
+void bph_shuffle(void *p, int *idx, int n)
+{
+    std::vector<int> v(idx, idx + n);
+    ((bphost::Host *)p)->shuffle(v);
+    for (int i = 0; i < n; i++) idx[i] = v[i];
+}
+// two-call protocol: in == NULL returns the sample count of the NEXT read without consuming anything is not possible
+// (the shuffle consumes random numbers), so the caller passes buffers sized traincache * dim.
+int bph_read_chunk(void *p, int idx, int cv, float *in, float *targ)
+{
+    bphost::Host *h = (bphost::Host *)p;
+    std::vector<float> a, b;
+    const int n = h->read_chunk(idx, cv != 0, a, b);
+    if (n < 0) return n;
+    memcpy(in, a.data(), a.size() * sizeof(float));
+    memcpy(targ, b.data(), b.size() * sizeof(float));
+    return n;
+}
+const float *bph_weights(void *p, int l) { return ((bphost::Host *)p)->W[l].data(); }
+const float *bph_bias(void *p, int l) { return ((bphost::Host *)p)->b[l].data(); }
+int bph_write_weights(void *p) { return ((bphost::Host *)p)->write_weights() ? 0 : -1; }
+}

@@ -51,6 +51,7 @@ private:
     std::vector<float> mean, dvar;
     std::vector<int> frames_before_sent, chunk_st, cv_chunk_st;
     int sent_st = 0, sent_en = 0, cv_sent_st = 0, cv_sent_en = 0;
+    unsigned long long rng_state = 0;     // drand48-family state (srand48 / lrand48, Interface.cc:411, 982)
 };
 
 }  // namespace bphost

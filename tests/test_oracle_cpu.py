@@ -1,0 +1,317 @@
+"""CPU tests: the oracle against the reference's golden vectors / known answers / the reference's own code."""
+import ctypes as C
+import math
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN, PKG_DIR, rel_err
+
+NAMES = ("TEST_DR8_MPAM0_SX289", "TEST_DR8_MPAM0_SX379")
+SEED = 27870775      # finetune.pl:31
+
+
+# ---------------------------------------------------------------- LPS
+@pytest.mark.parametrize("name,frames,samples", [(NAMES[0], 168, 43264), (NAMES[1], 156, 40192)])
+def test_lps_oracle_bit_exact_on_reference_goldens(oracle, name, frames, samples):
+    pcm = oracle.read_wav_pcm16(os.path.join(GOLDEN, name + ".wav"))
+    hdr, gold = oracle.read_htk(os.path.join(GOLDEN, name + ".lps"))
+    assert len(pcm) == samples and hdr == dict(nSamples=frames, sampPeriod=160000, sampSize=1028, parmKind=9)
+    mine = oracle.lps_extract(pcm)
+    assert mine.shape == (frames, 257)
+    assert np.array_equal(mine.view(np.uint32), gold.view(np.uint32))
+
+
+def test_lps_oracle_vs_reference_binary(oracle):
+    from oracle import refcuda
+    if not refcuda.available("Wav2LPS_be_ref"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.RandomState(1234)
+    pcm = np.clip(np.round(rng.randn(16000 * 5) * 3000), -32768, 32767).astype(np.int16)
+    ref, _ = refcuda.ref_wav2lps(pcm)
+    assert np.array_equal(oracle.lps_extract(pcm).view(np.uint32), ref.view(np.uint32))
+
+
+def test_lps_frame_count_and_floor(oracle):
+    L = oracle.lib()
+    assert [L.lps_oracle_nframes(n) for n in (0, 511, 512, 767, 768, 43264)] == [0, 0, 1, 1, 2, 168]
+    z = oracle.lps_extract(np.zeros(1024, np.int16))
+    assert z.shape == (3, 257) and np.all(z == -50.0)
+
+
+def test_rfft_matches_numpy(oracle):
+    rng = np.random.RandomState(0)
+    x = rng.randn(512).astype(np.float32)
+    y = x.copy()
+    oracle.lib().lps_oracle_rfft(y.ctypes.data_as(oracle.PF), 512, 9)
+    f = np.fft.rfft(x.astype(np.float64))
+    assert np.allclose(y[:257], f.real, atol=2e-4)
+    assert np.allclose(y[:256:-1], -f.imag[1:256], atol=2e-4) or np.allclose(y[:256:-1], f.imag[1:256], atol=2e-4)
+
+
+# ---------------------------------------------------------------- loader
+def _loader(oracle):
+    return oracle.PfileLoader(os.path.join(GOLDEN, "train_noisy.pfile"), os.path.join(GOLDEN, "train_clean.pfile"),
+                              os.path.join(GOLDEN, "train_noisy.norm"), 257, 7, 3, 102400, SEED)
+
+
+def test_loader_known_answers(oracle):
+    """numbers obtained with the reference's own Interface.cc on the bundled pfiles"""
+    feats, ends, _ = oracle.read_pfile(os.path.join(GOLDEN, "train_noisy.pfile"))
+    assert feats.shape == (1885, 257)
+    assert list(np.diff(np.concatenate([[0], ends]))) == [146, 143, 247, 227, 168, 177, 192, 191, 190, 204]
+    ld = _loader(oracle)
+    st, tot = ld.chunk_info(0, 7)
+    assert (len(st), tot) == (1, 1443)
+    cst, ctot = ld.chunk_info(8, 9)
+    assert (len(cst), ctot) == (1, 382)
+    x, t = ld.read_chunk(st, tot, 7, 0)
+    d = np.float64
+    assert abs(x.astype(d).sum() - 362738.279) < 0.01 and abs((x.astype(d) ** 2).sum() - 2543536.044) < 0.05
+    assert abs(t.astype(d).sum() - (-182261.062)) < 0.01 and abs((t.astype(d) ** 2).sum() - 451292.635) < 0.05
+    assert np.allclose(x[0, :4], [-1.032592, -0.154630, 0.140260, 0.258554], atol=1e-6)
+    assert abs(x[0, 771] - (-0.389783)) < 1e-6 and abs(t[0, 0] - (-0.555728)) < 1e-6
+
+
+def test_norm_file_is_mean_and_reciprocal_std(oracle):
+    feats, _, _ = oracle.read_pfile(os.path.join(GOLDEN, "train_noisy.pfile"))
+    mean, dvar = oracle.read_norm(os.path.join(GOLDEN, "train_noisy.norm"), 257)
+    assert np.allclose(mean, feats.astype(np.float64).mean(0), rtol=1e-5, atol=1e-5)
+    assert np.allclose(dvar, 1.0 / feats.astype(np.float64).std(0), rtol=1e-4)
+
+
+def _host_lib():
+    so = os.path.join(PKG_DIR, "host", "libbphost.so")
+    if not os.path.exists(so):
+        pytest.skip("host/libbphost.so not built")
+    L = C.CDLL(so)
+    L.bph_create.restype = C.c_void_p
+    L.bph_create.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.bph_destroy.argtypes = [C.c_void_p]
+    L.bph_chunk_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.bph_shuffle.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    L.bph_read_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, oracle_PF, oracle_PF]
+    L.bph_weights.restype = oracle_PF
+    L.bph_weights.argtypes = [C.c_void_p, C.c_int]
+    L.bph_write_weights.argtypes = [C.c_void_p]
+    return L
+
+
+oracle_PF = C.POINTER(C.c_float)
+
+
+def _flags(tmp_path, init, **over):
+    kw = dict(gpu_used=0, numlayers=4, layersizes="1799,32,16,257", bunchsize=128, MLflag=1, shapefactor=1.5, momentum=0.9,
+              weightcost=0.00001, lrate=0.1, fea_dim=257, fea_context=7, traincache=102400, init_randem_seed=SEED, targ_offset=3,
+              initwts_file=init, norm_file=os.path.join(GOLDEN, "train_noisy.norm"), fea_file=os.path.join(GOLDEN, "train_noisy.pfile"),
+              targ_file=os.path.join(GOLDEN, "train_clean.pfile"), outwts_file=str(tmp_path / "out.wts"), log_file=str(tmp_path / "x.log"),
+              train_sent_range="0-7", cv_sent_range="8-9", dropoutflag=0, visible_omit=0.1, hid_omit=0.1)
+    kw.update(over)
+    return kw
+
+
+def _argv(kw):
+    args = [b"BPtrain_Sigmoid"] + [("%s=%s" % (k, v)).encode() for k, v in kw.items()]
+    return len(args), (C.c_char_p * len(args))(*args)
+
+
+@pytest.mark.parametrize("traincache", [102400, 500])
+def test_product_host_loader_matches_restatement_and_reference(oracle, tmp_path, traincache):
+    """host/interface.cpp (product) vs the numpy restatement vs the reference's Interface.cc, bit for bit,
+    including multi-chunk splitting (traincache=500) and the lrand48 chunk/sample shuffles"""
+    L = _host_lib()
+    ls = [1799, 32, 16, 257]
+    W, b = oracle.init_weights(ls, seed=3)
+    init = str(tmp_path / "init.wts")
+    oracle.write_wts(init, ls, W, b)
+    kw = _flags(tmp_path, init, traincache=traincache)
+    h = L.bph_create(*_argv(kw))
+    assert h
+    for l in range(1, 4):
+        assert np.array_equal(np.ctypeslib.as_array(L.bph_weights(h, l), shape=(W[l - 1].size,)), W[l - 1])
+    nch, ns = C.c_int(), C.c_int()
+    assert L.bph_chunk_info(h, b"0-7", 0, C.byref(nch), C.byref(ns)) == 0
+    ld = oracle.PfileLoader(kw["fea_file"], kw["targ_file"], kw["norm_file"], 257, 7, 3, traincache, SEED)
+    st, tot = ld.chunk_info(0, 7)
+    assert (nch.value, ns.value) == (len(st), tot)
+    order_np = oracle.rand_index(list(range(len(st))), ld.rng)
+    order = (C.c_int * len(st))(*range(len(st)))
+    L.bph_shuffle(h, order, len(st))
+    assert list(order) == order_np
+    ref = None
+    from oracle import refcuda
+    if refcuda.available("libref_interface.so"):
+        kw2 = dict(kw); kw2["outwts_file"] = str(tmp_path / "ref.wts"); kw2["log_file"] = str(tmp_path / "ref.log")
+        ref = refcuda.RefInterface(**kw2)
+        assert ref.train_info("0-7") == (len(st), tot)
+        assert ref.shuffle_chunks(len(st)) == order_np
+    xin = np.zeros((traincache, 1799), np.float32); xt = np.zeros((traincache, 257), np.float32)
+    for ci in order_np:
+        n = L.bph_read_chunk(h, ci, 0, xin.ctypes.data_as(oracle_PF), xt.ctypes.data_as(oracle_PF))
+        x, t = ld.read_chunk(st, tot, 7, ci)
+        assert n == x.shape[0]
+        assert np.array_equal(xin[:n].view(np.uint32), x.view(np.uint32)) and np.array_equal(xt[:n].view(np.uint32), t.view(np.uint32))
+        if ref is not None:
+            xr, tr = ref.read_chunk(ci, 1799, 257)
+            assert xr.shape[0] == n and np.array_equal(xr.view(np.uint32), x.view(np.uint32)) and np.array_equal(tr.view(np.uint32), t.view(np.uint32))
+    # CV chunks: no shuffle
+    assert L.bph_chunk_info(h, b"8-9", 1, C.byref(nch), C.byref(ns)) == 0
+    cst, ctot = ld.chunk_info(8, 9)
+    assert (nch.value, ns.value) == (len(cst), ctot)
+    n = L.bph_read_chunk(h, 0, 1, xin.ctypes.data_as(oracle_PF), xt.ctypes.data_as(oracle_PF))
+    x, t = ld.read_chunk(cst, ctot, 9, 0, shuffle=False)
+    assert n == x.shape[0] and np.array_equal(xin[:n], x) and np.array_equal(xt[:n], t)
+    # weight file written by the product equals the oracle's writer (MAT-v4 layout, Interface.cc:489-514)
+    assert L.bph_write_weights(h) == 0
+    L.bph_destroy(h)
+    oracle.write_wts(str(tmp_path / "chk.wts"), ls, W, b)
+    assert open(kw["outwts_file"], "rb").read() == open(str(tmp_path / "chk.wts"), "rb").read()
+
+
+def test_host_loader_error_paths(oracle, tmp_path):
+    L = _host_lib()
+    ls = [1799, 32, 16, 257]
+    W, b = oracle.init_weights(ls, seed=3)
+    init = str(tmp_path / "init.wts")
+    oracle.write_wts(init, ls, W, b)
+    assert not L.bph_create(*_argv(_flags(tmp_path, init, layersizes="1799,32,17,257")))      # node counts do not match
+    assert "init weights node nums do not match" in open(str(tmp_path / "x.log")).read()
+    assert not L.bph_create(*_argv(_flags(tmp_path, init, fea_context=5)))                      # 257*5 != 1799
+    assert not L.bph_create(*_argv(_flags(tmp_path, init, fea_file="/nonexistent")))
+    h = L.bph_create(*_argv(_flags(tmp_path, init)))
+    a, c = C.c_int(), C.c_int()
+    assert L.bph_chunk_info(h, b"3-12", 0, C.byref(a), C.byref(c)) != 0                         # sentence 12 does not exist
+    assert L.bph_chunk_info(h, b"5", 0, C.byref(a), C.byref(c)) != 0                            # format error
+    L.bph_destroy(h)
+
+
+def test_file_format_round_trips(oracle, tmp_path):
+    rng = np.random.RandomState(2)
+    feats = rng.randn(57, 5).astype(np.float32)
+    oracle.write_pfile(str(tmp_path / "a.pfile"), feats, [20, 30, 7])
+    f2, ends, sid = oracle.read_pfile(str(tmp_path / "a.pfile"))
+    assert np.array_equal(f2, feats) and list(ends) == [20, 50, 57] and list(sid[[0, 19, 20, 56]]) == [0, 0, 1, 2]
+    ls = [6, 4, 3]
+    W, b = oracle.init_weights(ls, seed=1)
+    oracle.write_wts(str(tmp_path / "w.wts"), ls, W, b)
+    W2, b2 = oracle.read_wts(str(tmp_path / "w.wts"), ls)
+    assert all(np.array_equal(x, y) for x, y in zip(W + b, W2 + b2))
+    raw = open(str(tmp_path / "w.wts"), "rb").read()
+    assert np.frombuffer(raw[:20], "<i4").tolist() == [10, 4, 6, 0, 10] and raw[20:30] == b"weights12\0"
+    oracle.write_htk(str(tmp_path / "x.lps"), feats[:, :3])
+    hdr, f3 = oracle.read_htk(str(tmp_path / "x.lps"))
+    assert hdr["nSamples"] == 57 and hdr["sampSize"] == 12 and np.array_equal(f3, feats[:, :3])
+
+
+def test_rand48_matches_libc():
+    from oracle.oracle import Rand48
+    libc = C.CDLL("libc.so.6")
+    libc.lrand48.restype = C.c_long
+    libc.srand48(C.c_long(SEED))
+    r = Rand48(SEED)
+    assert [r.lrand48() for _ in range(1000)] == [libc.lrand48() for _ in range(1000)]
+
+
+# ---------------------------------------------------------------- training step
+def _numpy_step(ls, W, b, x, t, beta, ml):
+    """independent float64 restatement of forward + loss gradient (for a finite-difference-free check of the oracle)"""
+    M = x.shape[0]
+    ys = [x.astype(np.float64)]
+    for l in range(1, len(ls)):
+        Wm = W[l - 1].astype(np.float64).reshape(ls[l - 1], ls[l])
+        z = ys[-1] @ Wm + b[l - 1]
+        ys.append(z if l == len(ls) - 1 else 1.0 / (1.0 + np.exp(-z)))
+    e = ys[-1] - t
+    s = (np.abs(e) ** beta).sum(0)
+    alpha = (beta * s / M) ** (1.0 / beta)
+    if ml:
+        d = np.sign(e) * np.abs(e) ** (beta - 1) * beta / alpha ** beta / M
+        loss = np.log(alpha).sum() + (np.abs(e / alpha) ** beta).sum() / M
+    else:
+        d = beta * np.sign(e) * np.abs(e) ** (beta - 1) / M
+        loss = (np.abs(e) ** beta).sum() / M
+    grads = []
+    for l in range(len(ls) - 1, 0, -1):
+        grads.append(ys[l - 1].T @ d)
+        if l > 1:
+            Wm = W[l - 1].astype(np.float64).reshape(ls[l - 1], ls[l])
+            d = (d @ Wm.T) * ys[l - 1] * (1 - ys[l - 1])
+    return ys[-1], alpha, loss, grads[::-1]
+
+
+@pytest.mark.parametrize("ml,beta", [(1, 1.5), (1, 1.0), (0, 2.0), (0, 1.3)])
+def test_oracle_step_against_float64_math(oracle, ml, beta):
+    ls, M = [20, 16, 12, 9], 32
+    rng = np.random.RandomState(4)
+    W, b = oracle.init_weights(ls, seed=5)
+    b = [rng.uniform(-0.2, 0.2, v.size).astype(np.float32) for v in b]
+    x = rng.randn(M, ls[0]).astype(np.float32); t = rng.randn(M, ls[-1]).astype(np.float32)
+    out, alpha, loss, grads = _numpy_step(ls, W, b, x, t, beta, ml)
+    net = oracle.OracleNet(ls, M, 0.1, 0.9, 1e-5, beta, ml, W, b)
+    net.train_bunch(x, t)
+    assert rel_err(net.out(M), out) < 1e-6
+    if ml:
+        assert rel_err(net.alpha(), alpha) < 1e-6
+    assert abs(net.last_loss() - loss) < 1e-5 * abs(loss)
+    for l in range(1, len(ls)):
+        assert rel_err(net.grad(l), grads[l - 1].reshape(-1)) < 2e-5
+    # update rule incl. the reference's 1/M^2 net scaling (dedx carries 1/M, kernUpdatedelta divides by n again)
+    Wn, bn = net.weights()
+    for l in range(1, len(ls)):
+        g = grads[l - 1].reshape(-1)
+        want = W[l - 1] + (-0.1 * (g / M + 1e-5 * W[l - 1]))
+        assert rel_err(Wn[l - 1] - W[l - 1], want - W[l - 1]) < 2e-3   # difference of float32 neighbours
+
+
+def test_oracle_momentum_and_tail_bunch(oracle):
+    ls, M = [10, 8, 5], 16
+    rng = np.random.RandomState(8)
+    W, b = oracle.init_weights(ls, seed=2)
+    x = rng.randn(3 * M + 5, ls[0]).astype(np.float32); t = rng.randn(3 * M + 5, ls[-1]).astype(np.float32)
+    net = oracle.OracleNet(ls, M, 0.1, 0.9, 0.0, 2.0, 0, W, b)
+    losses, _ = net.train(x, t)
+    assert len(losses) == 3                       # tail of 5 frames dropped (BP_GPU.cu:173-180)
+    net2 = oracle.OracleNet(ls, M, 0.1, 0.9, 0.0, 2.0, 0, W, b)
+    for i in range(3):
+        net2.train_bunch(x[i * M:(i + 1) * M], t[i * M:(i + 1) * M])
+    assert all(np.array_equal(a, c) for a, c in zip(net.weights()[0], net2.weights()[0]))
+    # CV processes the partial bunch (BP_GPU.cu:203-218)
+    assert net.forward(x).shape == (3 * M + 5, 5)
+
+
+def test_oracle_sharded_equals_unsharded(oracle):
+    ls, Mg = [24, 20, 11], 64
+    rng = np.random.RandomState(6)
+    W, b = oracle.init_weights(ls, seed=7)
+    x = rng.randn(Mg, ls[0]).astype(np.float32); t = rng.randn(Mg, ls[-1]).astype(np.float32)
+    for ml, beta in ((1, 1.5), (0, 2.0)):
+        a = oracle.OracleNet(ls, Mg, 0.1, 0.9, 1e-5, beta, ml, W, b)
+        a.train_bunch(x, t)
+        for world in (2, 4, 8):
+            s = oracle.OracleNet(ls, Mg // world, 0.1, 0.9, 1e-5, beta, ml, W, b)
+            s.train_bunch_sharded(world, x, t)
+            if ml:
+                assert rel_err(s.alpha(), a.alpha()) < 1e-6
+            for u, v in zip(s.weights()[0] + s.weights()[1], a.weights()[0] + a.weights()[1]):
+                assert rel_err(u, v) < 1e-6
+
+
+def test_gamma_polynomial(oracle):
+    L = oracle.lib()
+    for xv in (0.5, 2.0 / 3.0, 1.0, 1.5, 2.5, 3.7, 6.2):
+        assert abs(L.ggd_oracle_gamma(xv) - math.gamma(xv)) < 2e-5 * math.gamma(xv)   # polynomial approximation
+    assert L.ggd_oracle_gamma(-1.0) == 0.0
+
+
+def test_cv_metrics_definitions(oracle):
+    ls, M = [6, 5, 4], 8
+    rng = np.random.RandomState(1)
+    W, b = oracle.init_weights(ls, seed=1)
+    x = rng.randn(19, 6).astype(np.float32); t = rng.randn(19, 4).astype(np.float32)
+    net = oracle.OracleNet(ls, M, 0.1, 0.9, 0.0, 1.5, 1, W, b)
+    net.train_bunch(x[:M], t[:M])
+    out = net.forward(x).astype(np.float64)
+    al = net.alpha().astype(np.float64)
+    assert abs(net.cv_sqerr(x, t) - ((out - t) ** 2).sum()) < 1e-3
+    assert abs(net.cv_abserr(x, t) - np.abs(out - t).sum() / 4) < 1e-3
+    ll = 19 * 4 * math.log(1.5 / (2 * math.gamma(1 / 1.5))) - 19 * np.log(al).sum() - (np.abs((t - out) / al) ** 1.5).sum()
+    assert abs(net.cv_loglik(x, t) - ll) < 2e-3 * abs(ll)
