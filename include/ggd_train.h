@@ -131,6 +131,11 @@ int ggd_debug_read(ggd_handle *h, int what, int layer, float *dst);
 /* Raw tcgen05 GEMM probe (tests only): D[i][j] = sum_r A(i,r) B(j,r), fp32 host arrays.
  * a_mn / b_mn = 0: operand is [rows][R] (reduction contiguous); 1: operand is [R][rows]. */
 int ggd_debug_gemm(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, const float *A, const float *B, float *D);
+/* same, timed: `reps` back-to-back launches between CUDA events (avg_ms), plus an optional per-CTA trace of
+ * globaltimer stamps (trace_host[ctas][16]; slots: 0 entry, 1 setup done, 2 first stage issued, 3 first stage landed,
+ * 4 last stage landed, 5 last MMA issued, 6 accumulator ready, 7 cluster exchange done, 8 epilogue done, 9 exit) */
+int ggd_debug_gemm_timed(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, const float *A, const float *B, float *D,
+                         int reps, float *avg_ms, unsigned long long *trace_host, int trace_ctas);
 /* writes a 128-byte ncclUniqueId (rank 0 creates it, every rank passes it in ggd_config) */
 int ggd_nccl_unique_id(void *out128);
 

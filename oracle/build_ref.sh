@@ -74,7 +74,7 @@ if command -v nvcc >/dev/null; then
 fi
 # 3. the reference CUDA trainer for sm_100a (second baseline + strongest oracle; runs on the GPU box)
 if command -v nvcc >/dev/null; then
-  nvcc -w -O2 -gencode arch=compute_100a,code=sm_100a -I"$CUDA/include" -Xcompiler -fpermissive \
+  nvcc -w -gencode arch=compute_100a,code=sm_100a -I"$CUDA/include" -Xcompiler -fpermissive \
     -o "$OUT/BPtrain_ref" "$TMP/BPtrain.cc" "$TMP/Interface.cc" "$TMP/BP_GPU.cu" "$TMP/DevFunc.cu" \
     -lcublas -lcurand -lpthread || echo "reference CUDA trainer did not build"
 fi

@@ -38,6 +38,16 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t raddr, float a, float b, 
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void stamp(const GemmArgs &g, int slot)
+{
+    if (g.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        g.trace[(size_t)cta * 16 + slot] = t;
+    }
+}
+
 // ---- epilogues: 16 consecutive output columns [j, j+16) of output row i ----------------------------
 template <int EPI>
 __device__ __forceinline__ void epilogue16(const GemmArgs &g, int i, int j, float *v)
@@ -122,6 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int kb0 = (g.kblocks * rank) / S, kb1 = (g.kblocks * (rank + 1)) / S;
     const int nkb = kb1 - kb0;
     const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
+    if (threadIdx.x == 0) stamp(g, 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
@@ -140,6 +151,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x == 0) stamp(g, 1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -171,6 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         tma_load_2d(sb + B_TILE + h * 8192, &tm_b_lo, &full_bar[s], j0 + 64 * h, r0);
                     }
                 }
+                if (it == 0) stamp(g, 2);
             }
         }
         __syncwarp();
@@ -184,6 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                if (it == 0) stamp(g, 3);
+                if (it == nkb - 1) stamp(g, 4);
                 const uint32_t a_hi = smem_u32(smem + s * STAGE), a_lo = a_hi + A_TILE;
                 const uint32_t b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
@@ -199,12 +214,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs retire
             }
             umma_commit(&tmem_full_bar);
+            stamp(g, 5);
         }
         __syncwarp();
     } else {
         // ===== epilogue warps: wait for the accumulator =====
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) stamp(g, 6);
     }
 
     const int q = warp & 3;                 // TMEM lane quadrant of this warp
@@ -229,6 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
         cluster_sync_all();   // all partial slabs have landed
     }
+    if (threadIdx.x == 64) stamp(g, 7);
     if (warp >= 2) {
         for (int c = 0; c < W; c += 16) {
             float v[16];
@@ -245,9 +263,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             epilogue16<EPI>(g, i0 + row, j0 + rank * W + c, v);
         }
     }
+    if (threadIdx.x == 64) stamp(g, 8);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<BN>(tmem);
+    if (threadIdx.x == 0) stamp(g, 9);
 }
 
 // ---- host side -----------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ struct GemmArgs {
     int ld32;
     const bf16 *y_hi, *y_lo;  // EPI_DX_DSIGMOID: activations of the layer whose dE/dx is produced, pitch ldy
     int ldy;
+    unsigned long long *trace;   // optional [ctas][16] globaltimer stamps of the pipeline phases (ggd_debug_gemm_timed)
 };
 
 struct GemmPlan {

@@ -264,7 +264,6 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         if (h->tensor) {
             if (l != 1) { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
             { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
-            { ProfScope ps(h, KC_BIAS, s); launch_bias_grad(nullptr, h->dx_hi[l], h->dx_lo[l], ly.Np, h->M, ly.cur, h->G + ly.b_off, s); (*launches)++; }
         } else {
             if (l != L - 1) { launch_simt_dsigmoid(h->y32[l], h->dy32[l], h->dx32[l], ly.Np, h->M, ly.cur, s); (*launches)++; }
             if (l != 1) {
@@ -272,9 +271,22 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
                 (*launches)++;
             }
             launch_simt_gemm(h->y32[l - 1], 1, ly.Kp, h->dx32[l], 1, ly.Np, h->G + ly.w_off, ly.Np, ly.prev, ly.cur, h->M, s);
-            launch_bias_grad(h->dx32[l], nullptr, nullptr, ly.Np, h->M, ly.cur, h->G + ly.b_off, s);
-            (*launches) += 2;
+            (*launches)++;
         }
+    }
+    {
+        ProfScope ps(h, KC_BIAS, s);
+        BiasGradArgs ba;
+        memset(&ba, 0, sizeof ba);
+        ba.M = h->M;
+        for (int l = 1; l < L; l++) {
+            const LayerInfo &ly = h->lay[l];
+            BiasGradLayer &b = ba.layer[ba.nlayers++];
+            b.dx32 = h->tensor ? nullptr : h->dx32[l];
+            b.hi = h->tensor ? h->dx_hi[l] : nullptr; b.lo = h->tensor ? h->dx_lo[l] : nullptr;
+            b.ld = ly.Np; b.N = ly.cur; b.dst = h->G + ly.b_off;
+        }
+        launch_bias_grad(ba, s); (*launches)++;
     }
     if (h->has_comm) {
         // frame-sharded data parallelism: sum the weight and bias gradients of all ranks
@@ -292,10 +304,12 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         }
         ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
         ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
+        ua.ctl = h->ctl;   // the update kernel also advances the bunch counter
         ProfScope ps(h, KC_UPDATE, s);
         launch_update(ua, h->sm_count, s); (*launches)++;
+    } else {
+        ProfScope ps(h, KC_ADVANCE, s); launch_advance(h->ctl, s); (*launches)++;
     }
-    { ProfScope ps(h, KC_ADVANCE, s); launch_advance(h->ctl, s); (*launches)++; }
     GGD_CUDA(cudaGetLastError());
     return GGD_OK;
 }
@@ -762,6 +776,29 @@ int ggd_nccl_unique_id(void *out128)
     return GGD_OK;
 }
 
+static unsigned long long *g_gemm_trace = nullptr;   // set by ggd_debug_gemm_timed around ggd_debug_gemm
+static int g_gemm_reps = 1;
+static float g_gemm_ms = 0;
+
+int ggd_debug_gemm_timed(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, const float *A, const float *B, float *D,
+                         int reps, float *avg_ms, unsigned long long *trace_host, int trace_ctas)
+{
+    unsigned long long *dtrace = nullptr;
+    if (trace_host && trace_ctas > 0) {
+        if (cudaMalloc(&dtrace, (size_t)trace_ctas * 16 * 8) != cudaSuccess) { set_error("trace alloc failed"); return GGD_ENOMEM; }
+        cudaMemset(dtrace, 0, (size_t)trace_ctas * 16 * 8);
+    }
+    g_gemm_trace = dtrace; g_gemm_reps = reps > 0 ? reps : 1;
+    int rc = ggd_debug_gemm(a_mn, b_mn, I, J, R, bn, splits, A, B, D);
+    g_gemm_trace = nullptr; g_gemm_reps = 1;
+    if (avg_ms) *avg_ms = g_gemm_ms;
+    if (dtrace) {
+        if (rc == GGD_OK) cudaMemcpy(trace_host, dtrace, (size_t)trace_ctas * 16 * 8, cudaMemcpyDeviceToHost);
+        cudaFree(dtrace);
+    }
+    return rc;
+}
+
 int ggd_debug_gemm(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, const float *A, const float *B, float *D)
 {
     if (!A || !B || !D || I < 1 || J < 1 || R < 1) { set_error("ggd_debug_gemm: bad argument"); return GGD_EINVAL; }
@@ -799,6 +836,19 @@ int ggd_debug_gemm(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, 
     if (!rc) rc = launch_gemm_tc(p, 0);
     if (rc) { cleanup(); return rc; }
     DG(cudaDeviceSynchronize());
+    if (g_gemm_reps > 1) {   // warm timing: back-to-back launches between two events
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < g_gemm_reps && !rc; i++) rc = launch_gemm_tc(p, 0);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&g_gemm_ms, e0, e1);
+        g_gemm_ms /= g_gemm_reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (g_gemm_trace) { p.args.trace = g_gemm_trace; if (!rc) rc = launch_gemm_tc(p, 0); cudaDeviceSynchronize(); }   // traced launch, warm
+        if (rc) { cleanup(); return rc; }
+    }
     DG(cudaMemcpy2D(D, (size_t)J * 4, dD, (size_t)Jp * 4, (size_t)J * 4, I, cudaMemcpyDeviceToHost));
 #undef DG
     cleanup();

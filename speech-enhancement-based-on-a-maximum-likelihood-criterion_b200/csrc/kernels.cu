@@ -51,7 +51,7 @@ __device__ __forceinline__ float pow_abs(float a, float p)
 }
 
 constexpr int LOSS_COLS = 32;   // columns per block (one warp-wide coalesced row segment)
-constexpr int LOSS_ROWL = 8;    // row lanes per block
+constexpr int LOSS_ROWL = 32;   // row lanes per block (1024 threads: at M = 128 each thread owns 4 rows per column)
 
 __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
 {
@@ -146,23 +146,38 @@ void launch_loss(const LossArgs &a, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void bias_grad_kernel(const float *__restrict__ dx32, const bf16 *__restrict__ hi, const bf16 *__restrict__ lo,
-                                 int ld, int M, int N, float *__restrict__ dst)
+constexpr int BG_COLS = 32, BG_ROWL = 8;
+__global__ void __launch_bounds__(BG_COLS *BG_ROWL) bias_grad_kernel(const BiasGradArgs a)
 {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    __shared__ float red[BG_ROWL][BG_COLS + 1];
+    const BiasGradLayer L = a.layer[blockIdx.y];
+    const int tx = threadIdx.x % BG_COLS, ty = threadIdx.x / BG_COLS;
+    const int n = blockIdx.x * BG_COLS + tx;
+    if (blockIdx.x * BG_COLS >= L.N) return;
     float s = 0.0f;
-    if (dx32) {
-        for (int m = 0; m < M; m++) s += dx32[(size_t)m * ld + n];
-    } else {
-        for (int m = 0; m < M; m++) s += join_bf16(hi[(size_t)m * ld + n], lo[(size_t)m * ld + n]);
+    if (n < L.N) {
+        if (L.dx32) {
+            for (int m = ty; m < a.M; m += BG_ROWL) s += L.dx32[(size_t)m * L.ld + n];
+        } else {
+            for (int m = ty; m < a.M; m += BG_ROWL) s += join_bf16(L.hi[(size_t)m * L.ld + n], L.lo[(size_t)m * L.ld + n]);
+        }
     }
-    dst[n] = s;
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && n < L.N) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int r = 1; r < BG_ROWL; r++) t += red[r][tx];
+        L.dst[n] = t;
+    }
 }
 
-void launch_bias_grad(const float *dx32, const bf16 *dx_hi, const bf16 *dx_lo, int ld, int M, int N, float *dst, cudaStream_t s)
+void launch_bias_grad(const BiasGradArgs &a, cudaStream_t s)
 {
-    bias_grad_kernel<<<ceil_div(N, 64), 64, 0, s>>>(dx32, dx_hi, dx_lo, ld, M, N, dst);
+    int maxn = 0;
+    for (int l = 0; l < a.nlayers; l++) maxn = a.layer[l].N > maxn ? a.layer[l].N : maxn;
+    dim3 grid(ceil_div(maxn, BG_COLS), a.nlayers);
+    bias_grad_kernel<<<grid, BG_COLS * BG_ROWL, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,6 +191,9 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdArgs a)
     uint2 *Hi = reinterpret_cast<uint2 *>(a.Phi + sg.off);
     uint2 *Lo = reinterpret_cast<uint2 *>(a.Plo + sg.off);
     const float mom = a.mom, lr = a.lr, Mg = a.Mg, wc = sg.wc;
+    // last kernel of the step: move the device-side bunch counter on (no kernel of this step reads it any more,
+    // and the next step's kernels are stream-ordered behind this one)
+    if (a.ctl && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.ctl->bunch_idx += 1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 w = P[i], d = D[i];
         const float4 g = __ldcs(G + i);

@@ -39,8 +39,18 @@ struct LossArgs {
 };
 void launch_loss(const LossArgs &a, cudaStream_t s);
 
-// bias gradient: dst[n] = sum_{m<M} dedx[m][n]   (kernAccSumrow, DevFunc.cu:267-285)
-void launch_bias_grad(const float *dx32, const bf16 *dx_hi, const bf16 *dx_lo, int ld, int M, int N, float *dst, cudaStream_t s);
+// bias gradients of ALL layers in one launch: dst[n] = sum_{m<M} dedx[m][n]   (kernAccSumrow, DevFunc.cu:267-285)
+struct BiasGradLayer {
+    const float *dx32;          // fp32 deltas (validation path) or NULL
+    const bf16 *hi, *lo;        // bf16 hi/lo deltas
+    int ld, N;
+    float *dst;
+};
+struct BiasGradArgs {
+    BiasGradLayer layer[10];
+    int nlayers, M;
+};
+void launch_bias_grad(const BiasGradArgs &a, cudaStream_t s);
 
 struct UpdSeg {
     long long off;   // element offset in the parameter arena (multiple of 4)
@@ -55,6 +65,7 @@ struct UpdArgs {
     const float *G;      // gradients (same arena layout)
     bf16 *Phi, *Plo;     // bf16 split shadows of P (weights only)
     float mom, lr, Mg;
+    StepCtl *ctl;        // when set, the kernel also advances ctl->bunch_idx (it is the last kernel of a step)
 };
 // kernUpdatedelta + kernAccSum fused (DevFunc.cu:490-507, 427-443)
 void launch_update(const UpdArgs &a, int sm_count, cudaStream_t s);
