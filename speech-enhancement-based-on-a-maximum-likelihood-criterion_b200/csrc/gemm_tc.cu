@@ -228,19 +228,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int row = q * 32 + lane;          // output row inside the tile
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const int W = BN / S;                   // columns owned by each CTA of the cluster
-    float *recv = reinterpret_cast<float *>(smem);   // [S][128][W], aliases the (drained) pipeline stages
+    // receive buffer [S][W/4][128] float4, aliases the (drained) pipeline stages.  The row index is the fastest
+    // dimension so that the 32 lanes of a warp write 512 contiguous bytes per remote store instruction.
+    float4 *recv = reinterpret_cast<float4 *>(smem);
+    const int W4 = W >> 2;
 
     if (S > 1) {
         cluster_sync_all();   // every CTA of the cluster has retired its MMAs: stage memory is free everywhere
         if (warp >= 2) {
             for (int p = 0; p < S; p++) {
                 if (p == rank) continue;
+                const uint32_t dst0 = map_to_cta(smem_u32(recv + ((size_t)rank * W4) * TILE_I + row), p);
                 for (int c = 0; c < W; c += 16) {
                     float v[16];
                     tmem_ld16(trow + p * W + c, v);
-                    const uint32_t dst = map_to_cta(smem_u32(recv + ((size_t)rank * TILE_I + row) * W + c), p);
 #pragma unroll
-                    for (int e = 0; e < 4; e++) st_cluster_f4(dst + 16 * e, v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                    for (int e = 0; e < 4; e++)
+                        st_cluster_f4(dst0 + (uint32_t)(((c >> 2) + e) * TILE_I) * 16u, v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
                 }
             }
         }
@@ -253,10 +257,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             tmem_ld16(trow + rank * W + c, v);
             for (int p = 0; p < S; p++) {
                 if (p == rank) continue;
-                const float4 *src = reinterpret_cast<const float4 *>(recv + ((size_t)p * TILE_I + row) * W + c);
+                const float4 *src = recv + ((size_t)p * W4 + (c >> 2)) * TILE_I + row;
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const float4 t = src[e];
+                    const float4 t = src[e * TILE_I];
                     v[4 * e] += t.x; v[4 * e + 1] += t.y; v[4 * e + 2] += t.z; v[4 * e + 3] += t.w;
                 }
             }
@@ -321,7 +325,7 @@ static int launch_bn(const GemmPlan &p, cudaStream_t s)
 
 int launch_gemm_tc(const GemmPlan &p, cudaStream_t s)
 {
-    if (p.splits < 1 || p.splits > 8 || (p.bn / p.splits) % 16 != 0 || p.splits > p.args.kblocks) {
+    if (p.splits < 1 || p.splits > 8 || (p.splits & (p.splits - 1)) || (p.bn / p.splits) % 16 != 0 || p.splits > p.args.kblocks) {
         set_error("gemm_tc: bad split %d for bn=%d kblocks=%d", p.splits, p.bn, p.args.kblocks);
         return GGD_EINVAL;
     }

@@ -116,12 +116,27 @@ static void free_chunk(ggd_handle *h)
     if (h->gN) { cudaGraphExecDestroy(h->gN); h->gN = nullptr; }
 }
 
-static int pick_splits(int tiles, int bn, int kblocks, int sm)
+// Tile width and cluster split of one GEMM.  Measured on B200 (tools/gemm_probe.py): an SM pulls ~100 GB/s through
+// TMA, clusters of 8 CTAs with ~200 KB of shared memory each only co-schedule 64 CTAs (two waves), and the
+// DSMEM reduce-scatter costs ~1 us per 8 KB received.  The model below picks (bn, S) with S <= 4 accordingly.
+static void pick_tile(int tiles_i, int Np, int kblocks, int sm, int *bn_out, int *splits_out)
 {
-    int best = 1;
-    for (int s = 2; s <= 8; s *= 2)
-        if (s <= kblocks && (bn / s) % 16 == 0 && tiles * s <= sm + sm / 8) best = s;
-    return best;
+    double best = 1e30;
+    *bn_out = 64; *splits_out = 1;
+    for (int bn = 64; bn <= 128; bn += 64) {
+        if (Np % bn) continue;
+        for (int s = 1; s <= 4; s *= 2) {
+            if (s > kblocks || (bn / s) % 16) continue;
+            const int ctas = tiles_i * (Np / bn) * s;
+            const int waves = (ctas + sm - 1) / sm;
+            const double stage_kb = 32.0 + bn * 0.25;                       // A hi/lo + B hi/lo per k-block
+            const double kb_per_cta = (double)((kblocks + s - 1) / s);
+            const double t_main = 1.3 + kb_per_cta * stage_kb / 100.0;       // us: latency + bytes at ~100 KB/us per SM
+            const double t_xchg = (s > 1) ? 0.8 + (s - 1) * (128.0 * (bn / s) * 4.0 / 1024.0) / 16.0 : 0.0;
+            const double t = waves * (t_main + t_xchg + 1.0 + bn / 128.0);
+            if (t < best) { best = t; *bn_out = bn; *splits_out = s; }
+        }
+    }
 }
 
 // (re)build tensor maps and GEMM plans; needs the chunk buffers for the layer-1 operands
@@ -137,7 +152,7 @@ static int build_plans(ggd_handle *h)
         {
             GemmPlan &p = h->fwd[l];
             memset(&p, 0, sizeof p);
-            p.bn = (ly.Np % 128 == 0) ? 128 : 64;
+            pick_tile(h->Mp / 128, ly.Np, ly.Kp / 64, h->sm_count, &p.bn, &p.splits);
             p.a_mn = 0; p.b_mn = 1;
             p.epi = last ? EPI_FWD_LINEAR : EPI_FWD_SIGMOID;
             p.tiles_i = h->Mp / 128; p.tiles_j = ly.Np / p.bn;
@@ -151,13 +166,12 @@ static int build_plans(ggd_handle *h)
             a.bias = h->P + ly.b_off;
             a.o_hi = h->act_hi[l]; a.o_lo = h->act_lo[l]; a.ldo = ly.Np;
             a.o32 = h->out32; a.ld32 = ly.Np;
-            p.splits = pick_splits(p.tiles_i * p.tiles_j, p.bn, a.kblocks, h->sm_count);
         }
         // ---- backward: dE/dy[m][k] = sum_n dE/dx[m][n] W[k][n], times y(1-y) of layer l-1
         if (!first) {
             GemmPlan &p = h->dxp[l];
             memset(&p, 0, sizeof p);
-            p.bn = (ly.Kp % 128 == 0) ? 128 : 64;
+            pick_tile(h->Mp / 128, ly.Kp, ly.Np / 64, h->sm_count, &p.bn, &p.splits);
             p.a_mn = 0; p.b_mn = 0;
             p.epi = EPI_DX_DSIGMOID;
             p.tiles_i = h->Mp / 128; p.tiles_j = ly.Kp / p.bn;
@@ -170,7 +184,6 @@ static int build_plans(ggd_handle *h)
             a.I = h->M; a.J = ly.prev; a.kblocks = ly.Np / 64;
             a.o_hi = h->dx_hi[l - 1]; a.o_lo = h->dx_lo[l - 1]; a.ldo = ly.Kp;
             a.y_hi = h->act_hi[l - 1]; a.y_lo = h->act_lo[l - 1]; a.ldy = ly.Kp;
-            p.splits = pick_splits(p.tiles_i * p.tiles_j, p.bn, a.kblocks, h->sm_count);
         }
         // ---- gradient: g[k][n] = sum_m y[m][k] dE/dx[m][n]
         {
