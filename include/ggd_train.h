@@ -81,6 +81,10 @@ typedef struct ggd_handle ggd_handle;
 int ggd_create(const ggd_config *cfg, const float *const *weights, const float *const *bias, ggd_handle **out);
 int ggd_destroy(ggd_handle *h);
 
+/* Optional: allocate the chunk staging for up to n_frames and capture the step graphs now instead of inside
+ * the first ggd_train* call (the reference allocates for MAXCACHEFRAME in its constructor, BP_GPU.cu:72-75). */
+int ggd_reserve(ggd_handle *h, int n_frames);
+
 /* One call = one chunk: H2D copy, then one training step per full bunch; a trailing partial bunch is
  * dropped (BP_GPU.cu:173-180).  Blocking, like the reference. */
 int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ);

@@ -54,6 +54,7 @@ def load_library():
         L.ggd_create.argtypes = [C.POINTER(_Config), C.POINTER(PF), C.POINTER(PF), C.POINTER(C.c_void_p)]
         L.ggd_destroy.argtypes = [C.c_void_p]
         L.ggd_train.argtypes = [C.c_void_p, C.c_int, PF, PF]
+        L.ggd_reserve.argtypes = [C.c_void_p, C.c_int]
         L.ggd_train_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         for f in ("ggd_cv_sqerr", "ggd_cv_abserr", "ggd_cv_loglik"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int, PF, PF, PF]
@@ -166,6 +167,9 @@ class BP_GPU:
             Wp[l], bp[l] = _fp(W[l]), _fp(b[l])
         self._ck(self.L.ggd_get_weights(self.h, Wp, bp))
         return W[1:], b[1:]
+
+    def reserve(self, n_frames):
+        self._ck(self.L.ggd_reserve(self.h, int(n_frames)))
 
     # ---- additions (same handle) ---------------------------------------------------------------
     def train_device(self, n_frames, d_in_ptr, d_targ_ptr):

@@ -514,6 +514,21 @@ int ggd_destroy(ggd_handle *h)
     return GGD_OK;
 }
 
+int ggd_reserve(ggd_handle *h, int n_frames)
+{
+    if (!h || n_frames < 1 || n_frames > GGD_MAXCACHEFRAME) { set_error("ggd_reserve: bad argument"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    if (!(h->cfg.flags & GGD_FLAG_NO_GRAPH) && !h->g1) {
+        GGD_TRY(set_ctl(h, h->c_in, h->c_targ));
+        GGD_TRY(capture_graph(h, 1, &h->g1));
+        h->gN_steps = 16;
+        GGD_TRY(capture_graph(h, h->gN_steps, &h->gN));
+    }
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    return GGD_OK;
+}
+
 int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ)
 {
     if (!h || !in || !targ || n_frames < 0) { set_error("ggd_train: bad argument"); return GGD_EINVAL; }

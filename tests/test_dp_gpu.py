@@ -1,0 +1,70 @@
+"""Frame-sharded data parallelism on real GPUs (needs >= 2 devices; `gpurun --gpus 2`): two ranks, each training on
+its shard with NCCL allreduce of sum|e|^beta and of the gradients, must reproduce the unsharded global minibatch."""
+import os
+import sys
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LS, MS, NB = [70, 96, 80, 33], 128, 6
+
+
+def _data(world):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    rng = np.random.RandomState(13)
+    W, b = O.init_weights(LS, seed=3)
+    x = rng.randn(world, NB * MS, LS[0]).astype(np.float32)     # [rank][frames][dim]
+    t = rng.randn(world, NB * MS, LS[-1]).astype(np.float32)
+    return W, b, x, t
+
+
+def _rank(rank, world, uid, ml, beta, precision, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_pkg
+    pkg = load_pkg()
+    W, b, x, t = _data(world)
+    net = pkg.BP_GPU(0, rank, len(LS), LS, MS, 0.1, 0.9, 1e-5, W, b, beta, ml, precision=precision, world_size=world, rank=rank,
+                     nccl_unique_id=uid)
+    net.train(NB * MS, x[rank], t[rank])
+    Wn, bn = net.returnWeights()
+    q.put((rank, [w.copy() for w in Wn], [v.copy() for v in bn], net.alpha(), net.losses()))
+    net.close()
+
+
+@pytest.mark.parametrize("ml,beta,precision", [(1, 1.5, 0), (1, 1.5, 1), (0, 2.0, 0)])
+def test_two_gpu_dp_equals_unsharded(pkg, oracle, ml, beta, precision):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from se_ml_b200.bp_gpu import nccl_unique_id
+    world = 2
+    uid = nccl_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_rank, args=(r, world, uid, ml, beta, precision, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(60)
+    W, b, x, t = _data(world)
+    # unsharded equivalent: global minibatch = rank 0's bunch followed by rank 1's bunch
+    xg = np.concatenate([x[:, i * MS:(i + 1) * MS].reshape(world * MS, -1) for i in range(NB)])
+    tg = np.concatenate([t[:, i * MS:(i + 1) * MS].reshape(world * MS, -1) for i in range(NB)])
+    orc = oracle.OracleNet(LS, world * MS, 0.1, 0.9, 1e-5, beta, ml, W, b)
+    lo, al = orc.train(xg, tg)
+    Wo, bo = orc.weights()
+    tol = 1e-3 if precision == 0 else 1e-4
+    for r in res:
+        for a, c in zip(r[1] + r[2], Wo + bo):
+            assert np.linalg.norm(a - c) <= tol * max(np.linalg.norm(c), 1e-6)
+        if ml:
+            assert np.linalg.norm(r[3] - al[-1]) <= tol * np.linalg.norm(al[-1])     # alpha of the GLOBAL minibatch
+            assert np.allclose(r[4], lo, rtol=5e-3)
+    # both ranks hold identical weights
+    for a, c in zip(res[0][1], res[1][1]):
+        assert np.array_equal(a, c)
