@@ -233,6 +233,10 @@ def main():
         if k in gemm_flops:
             ent["tflops"] = gemm_flops[k] / (msk * 1e-3) / 1e12
             ent["frac_of_bf16_sustained"] = ent["tflops"] / peaks["bf16_sus"]
+        if k == "dw_update":
+            Ppad = kt["param_elems"]      # padded weights + biases; the fused kernel streams W and delta once each way
+            ent["gbs"] = 16.0 * Ppad / (msk * 1e-3) / 1e9
+            ent["tflops"] = gemm_flops["dw_gemm"] / (msk * 1e-3) / 1e12
         if k == "update":
             ent["gbs"] = 20.0 * kt["param_elems"] / (msk * 1e-3) / 1e9     # read W, delta, g; write W, delta (+4 B shadows not counted)
         if k == "loss":

@@ -68,8 +68,8 @@ typedef struct ggd_config {
 } ggd_config;
 
 enum {
-    GGD_FLAG_UNFUSED_UPDATE = 1,  /* materialise the weight gradient and run the stand-alone update kernel
-                                     (always the case when world_size > 1) */
+    GGD_FLAG_UNFUSED_UPDATE = 1,  /* materialise the weight gradient and run the stand-alone update kernel instead of the
+                                     fused gradient+update kernel (always the case when world_size > 1) */
     GGD_FLAG_NO_GRAPH = 2,        /* launch kernels directly instead of replaying a CUDA graph */
     GGD_FLAG_KEEP_DEBUG = 4,      /* keep per-step tensors readable through ggd_debug_read */
     GGD_FLAG_PIN_HOST = 8         /* cudaHostRegister the caller's (long-lived, reused) chunk buffers on first use;
@@ -117,7 +117,7 @@ int ggd_get_stats(ggd_handle *h, ggd_stats *s);
  * around every launch on the compute stream, and returns the summed milliseconds and launch counts per
  * kernel class (this is what bench.py divides the algorithmic bytes / FLOPs by). */
 enum { GGD_KC_FWD = 0, GGD_KC_LOSS, GGD_KC_DX, GGD_KC_DW, GGD_KC_BIAS, GGD_KC_ALLREDUCE, GGD_KC_UPDATE, GGD_KC_ADVANCE,
-       GGD_KC_SPLIT, GGD_KC_COUNT };
+       GGD_KC_SPLIT, GGD_KC_DWUPD, GGD_KC_COUNT };
 typedef struct ggd_kernel_times {
     double ms[16];
     long long launches[16];

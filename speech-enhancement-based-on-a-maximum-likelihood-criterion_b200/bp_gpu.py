@@ -34,7 +34,7 @@ class KernelTimes(C.Structure):
     _fields_ = [("ms", C.c_double * 16), ("launches", C.c_longlong * 16), ("steps", C.c_longlong), ("param_elems", C.c_longlong)]
 
 
-KERNEL_CLASSES = ("fwd_gemm", "loss", "dx_gemm", "dw_gemm", "bias_grad", "allreduce", "update", "advance", "split")
+KERNEL_CLASSES = ("fwd_gemm", "loss", "dx_gemm", "dw_gemm", "bias_grad", "allreduce", "update", "advance", "split", "dw_update")
 
 
 def library_path():

@@ -291,6 +291,23 @@ int make_tmap_bf16(CUtensorMap *m, const bf16 *base, long long rows, long long c
     return GGD_OK;
 }
 
+int make_tmap_2d(CUtensorMap *m, const void *base, int dtype_f32, long long rows, long long cols, long long ld, int box_cols, int box_rows,
+                 int swizzle128)
+{
+    if (!g_encode) { set_error("tensor-map encoder not initialised"); return GGD_ECUDA; }
+    const size_t es = dtype_f32 ? 4 : 2;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = g_encode(m, dtype_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, rows, cols, ld, box_cols, box_rows); return GGD_ECUDA; }
+    return GGD_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_inst(const GemmPlan &p, cudaStream_t s)
 {

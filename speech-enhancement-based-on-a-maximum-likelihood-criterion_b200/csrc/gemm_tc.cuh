@@ -52,7 +52,33 @@ struct GemmPlan {
 // 2-D bf16 row-major tensor [rows][cols] (pitch ld elements) with a {64, box_rows} box, 128-byte swizzle
 int make_tmap_bf16(CUtensorMap *m, const bf16 *base, long long rows, long long cols, long long ld, int box_rows);
 
+// generic 2-D row-major tensor map: fp32 (dtype_f32 = 1) or bf16 elements, {box_cols, box_rows} box, optional 128-byte swizzle
+int make_tmap_2d(CUtensorMap *m, const void *base, int dtype_f32, long long rows, long long cols, long long ld, int box_cols, int box_rows,
+                 int swizzle128);
+
 int launch_gemm_tc(const GemmPlan &p, cudaStream_t s);
+
+// ---- fused gradient GEMM + momentum-SGD update (dw_update.cu) ------------------------------------------------------
+// g[k][n] = sum_m y[m][k] dx[m][n] for one 128 x 64 tile of a weight matrix stays on chip (TMEM -> shared memory) and
+// is consumed at once by  delta <- mom*delta - lr*(g/Mg + wc*W);  W <- W + delta  (kernUpdatedelta + kernAccSum,
+// DevFunc.cu:490-507, 427-443), with W / delta tiles moved by TMA in both directions: 16 B/param of HBM traffic
+// (+4 B/param for the bf16 hi/lo operand shadows) instead of 28 when the gradient is materialised.
+struct DwUpdArgs {
+    const StepCtl *ctl;
+    int a_rows_from_ctl, rows_per_bunch;
+    int kblocks;              // frames / 64
+    int Kp, Np;
+    bf16 *w_hi, *w_lo;        // shadows, pitch Np
+    float mom, lr, Mg, wc;
+};
+struct DwUpdPlan {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;   // operands (bf16, MN-major boxes)
+    CUtensorMap w, d;                     // fp32 W and delta tiles (load + store)
+    DwUpdArgs args;
+    int tiles_i, tiles_j;
+};
+int launch_dw_update(const DwUpdPlan &p, cudaStream_t s);
+int dw_update_init();
 int gemm_tc_init();   // resolves the driver entry point, sets the shared-memory attributes
 
 }  // namespace ggd

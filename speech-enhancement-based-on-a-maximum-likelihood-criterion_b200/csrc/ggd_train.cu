@@ -77,6 +77,8 @@ struct ggd_handle {
     cudaEvent_t ev0, ev1, ev2;
     // plans + graphs
     GemmPlan fwd[GGD_MAXLAYER], dxp[GGD_MAXLAYER], dwp[GGD_MAXLAYER];
+    DwUpdPlan dwu[GGD_MAXLAYER];
+    bool fused;         // gradient GEMM + update fused (single GPU, tensor path)
     cudaGraphExec_t g1, gN;
     int gN_steps;
     int launches_per_step;
@@ -93,7 +95,7 @@ struct ggd_handle {
     std::vector<int> prof_cls;
 };
 
-enum { KC_FWD = 0, KC_LOSS, KC_DX, KC_DW, KC_BIAS, KC_ALLREDUCE, KC_UPDATE, KC_ADVANCE, KC_SPLIT, KC_COUNT };
+enum { KC_FWD = 0, KC_LOSS, KC_DX, KC_DW, KC_BIAS, KC_ALLREDUCE, KC_UPDATE, KC_ADVANCE, KC_SPLIT, KC_DWUPD, KC_COUNT };
 
 struct ProfScope {
     ggd_handle *h; cudaStream_t s;
@@ -203,6 +205,23 @@ static int build_plans(ggd_handle *h)
             a.o32 = h->G + ly.w_off; a.ld32 = ly.Np;
             p.splits = 1;
         }
+        // ---- fused gradient + update
+        {
+            DwUpdPlan &p = h->dwu[l];
+            memset(&p, 0, sizeof p);
+            p.tiles_i = ceil_div(ly.Kp, 128); p.tiles_j = ly.Np / 64;
+            GGD_TRY(make_tmap_bf16(&p.a_hi, ah, arows, ly.Kp, ly.Kp, 64));
+            GGD_TRY(make_tmap_bf16(&p.a_lo, al, arows, ly.Kp, ly.Kp, 64));
+            GGD_TRY(make_tmap_bf16(&p.b_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 64));
+            GGD_TRY(make_tmap_bf16(&p.b_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 64));
+            GGD_TRY(make_tmap_2d(&p.w, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 64, 128, 0));
+            GGD_TRY(make_tmap_2d(&p.d, h->Dl + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 64, 128, 0));
+            DwUpdArgs &a = p.args;
+            a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
+            a.kblocks = h->Mp / 64; a.Kp = ly.Kp; a.Np = ly.Np;
+            a.w_hi = h->Phi + ly.w_off; a.w_lo = h->Plo + ly.w_off;
+            a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg; a.wc = h->cfg.weightcost;
+        }
     }
     return GGD_OK;
 }
@@ -249,8 +268,9 @@ static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches)
     return GGD_OK;
 }
 
-static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *launches)
+static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *launches, bool allow_fused = true)
 {
+    const bool fused = h->fused && allow_fused && apply_update;
     const int L = h->L;
     const LayerInfo &top = h->lay[L - 1];
     GGD_TRY(enqueue_forward(h, s, launches));
@@ -276,7 +296,8 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         const LayerInfo &ly = h->lay[l];
         if (h->tensor) {
             if (l != 1) { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
-            { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
+            if (fused) { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_update(h->dwu[l], s)); (*launches)++; }
+            else { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
         } else {
             if (l != L - 1) { launch_simt_dsigmoid(h->y32[l], h->dy32[l], h->dx32[l], ly.Np, h->M, ly.cur, s); (*launches)++; }
             if (l != 1) {
@@ -298,9 +319,14 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             b.dx32 = h->tensor ? nullptr : h->dx32[l];
             b.hi = h->tensor ? h->dx_hi[l] : nullptr; b.lo = h->tensor ? h->dx_lo[l] : nullptr;
             b.ld = ly.Np; b.N = ly.cur; b.dst = h->G + ly.b_off;
+            b.b = h->P + ly.b_off; b.db = h->Dl + ly.b_off;
+        }
+        if (fused) {   // biases are updated right here and this is the last kernel of the step
+            ba.apply = 1; ba.mom = h->cfg.momentum; ba.lr = h->cfg.lrate; ba.Mg = (float)h->Mg; ba.ctl = h->ctl;
         }
         launch_bias_grad(ba, s); (*launches)++;
     }
+    if (fused) { GGD_CUDA(cudaGetLastError()); return GGD_OK; }
     if (h->has_comm) {
         // frame-sharded data parallelism: sum the weight and bias gradients of all ranks
         ProfScope ps(h, KC_ALLREDUCE, s);
@@ -428,6 +454,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     h->L = cfg->numlayers; h->M = cfg->bunchsize; h->Mp = round_up(h->M, 128);
     h->sm_count = prop.multiProcessorCount;
     h->tensor = (cfg->precision == GGD_PREC_BF16X3);
+    h->fused = h->tensor && !(cfg->world_size > 1) && !(cfg->flags & GGD_FLAG_UNFUSED_UPDATE);
     const int world = cfg->world_size > 1 ? cfg->world_size : 1;
     h->Mg = h->M * world;
     size_t off = 0;
@@ -478,7 +505,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         launch_split_rows(h->P + ly.w_off, ly.Kp, ly.Np, h->Phi + ly.w_off, h->Plo + ly.w_off, ly.Np, 0);
     }
     CK(cudaDeviceSynchronize());
-    if (h->tensor) { int rc = gemm_tc_init(); if (rc != GGD_OK) return fail(rc); }
+    if (h->tensor) { int rc = gemm_tc_init(); if (rc == GGD_OK) rc = dw_update_init(); if (rc != GGD_OK) return fail(rc); }
     if (world > 1) {
         if (!cfg->nccl_unique_id) { set_error("world_size > 1 needs nccl_unique_id"); return fail(GGD_EINVAL); }
         ncclUniqueId id;
@@ -709,7 +736,7 @@ int ggd_debug_step(ggd_handle *h, int n_frames, const float *in, const float *ta
     GGD_CUDA(cudaMemsetAsync(h->trace, 0, h->trace_cap * sizeof(double), h->s_main));
     if (h->tensor) launch_split_rows(h->c_in, n_frames, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main);
     int launches = 0;
-    GGD_TRY(enqueue_step(h, h->s_main, apply_update != 0, &launches));
+    GGD_TRY(enqueue_step(h, h->s_main, apply_update != 0, &launches, false));   // unfused: the gradient stays readable
     double tr = 0;
     GGD_CUDA(cudaMemcpyAsync(&tr, h->trace, sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
     GGD_CUDA(cudaStreamSynchronize(h->s_main));

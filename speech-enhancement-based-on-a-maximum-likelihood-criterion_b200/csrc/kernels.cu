@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(BG_COLS *BG_ROWL) bias_grad_kernel(const BiasG
     const BiasGradLayer L = a.layer[blockIdx.y];
     const int tx = threadIdx.x % BG_COLS, ty = threadIdx.x / BG_COLS;
     const int n = blockIdx.x * BG_COLS + tx;
+    if (a.ctl && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.ctl->bunch_idx += 1;
     if (blockIdx.x * BG_COLS >= L.N) return;
     float s = 0.0f;
     if (n < L.N) {
@@ -168,7 +169,13 @@ __global__ void __launch_bounds__(BG_COLS *BG_ROWL) bias_grad_kernel(const BiasG
         float t = red[0][tx];
 #pragma unroll
         for (int r = 1; r < BG_ROWL; r++) t += red[r][tx];
-        L.dst[n] = t;
+        if (a.apply) {
+            const float d = a.mom * L.db[n] - a.lr * (t / a.Mg);
+            L.db[n] = d;
+            L.b[n] = d + L.b[n];
+        } else {
+            L.dst[n] = t;
+        }
     }
 }
 

@@ -44,11 +44,15 @@ struct BiasGradLayer {
     const float *dx32;          // fp32 deltas (validation path) or NULL
     const bf16 *hi, *lo;        // bf16 hi/lo deltas
     int ld, N;
-    float *dst;
+    float *dst;                 // gradient out (unfused path)
+    float *b, *db;              // bias and its momentum (fused path: updated in place)
 };
 struct BiasGradArgs {
     BiasGradLayer layer[10];
     int nlayers, M;
+    int apply;                  // 1: apply the momentum-SGD update to the biases here (no weight cost, BP_GPU.cu:435)
+    float mom, lr, Mg;
+    StepCtl *ctl;               // when set (last kernel of a fused step) the kernel advances ctl->bunch_idx
 };
 void launch_bias_grad(const BiasGradArgs &a, cudaStream_t s);
 

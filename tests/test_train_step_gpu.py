@@ -118,3 +118,25 @@ def test_named_shape_step(pkg, oracle):
     Wo, _ = orc.weights()
     for l in range(4):
         assert rel_err(Wg[l], Wo[l]) < 1e-3
+
+
+def test_fused_update_equals_unfused(pkg, oracle):
+    """the fused gradient-GEMM + update kernel (TMEM -> smem -> TMA store) against the materialised-gradient path"""
+    O = oracle
+    layersizes, M, nb = [7 * 33, 200, 130, 33], 128, 9     # ragged: Kp = 256/256/192, not multiples of 128 everywhere
+    W, b, x, t = make_case(O, layersizes, M * nb, 17)
+    res = []
+    for flags in (0, pkg.FLAG_UNFUSED_UPDATE):
+        net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1, flags=flags)
+        net.train(x.shape[0], x, t)
+        res.append((net.returnWeights(), net.alpha(), net.losses()))
+        net.close()
+    (Wa, ba), aa, la = res[0]
+    (Wb, bb), ab, lb = res[1]
+    for u, v in zip(Wa + ba, Wb + bb):
+        assert rel_err(u, v) < 1e-6
+    assert rel_err(aa, ab) < 1e-6 and np.allclose(la, lb, rtol=1e-6)
+    orc = O.OracleNet(layersizes, M, 0.1, 0.9, 1e-5, 1.5, 1, W, b)
+    orc.train(x, t)
+    for u, v in zip(Wa + ba, orc.weights()[0] + orc.weights()[1]):
+        assert rel_err(u, v) < 1e-3
