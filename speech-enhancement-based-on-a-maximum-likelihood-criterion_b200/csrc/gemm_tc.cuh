@@ -61,21 +61,22 @@ int launch_gemm_tc(const GemmPlan &p, cudaStream_t s);
 // ---- fused gradient GEMM + momentum-SGD update (dw_update.cu) ------------------------------------------------------
 // g[k][n] = sum_m y[m][k] dx[m][n] for one 128 x 64 tile of a weight matrix stays on chip (TMEM -> shared memory) and
 // is consumed at once by  delta <- mom*delta - lr*(g/Mg + wc*W);  W <- W + delta  (kernUpdatedelta + kernAccSum,
-// DevFunc.cu:490-507, 427-443), with W / delta tiles moved by TMA in both directions: 16 B/param of HBM traffic
+// DevFunc.cu:490-507, 427-443) with coalesced row-wise W / delta traffic: 16 B/param of HBM traffic
 // (+4 B/param for the bf16 hi/lo operand shadows) instead of 28 when the gradient is materialised.
 struct DwUpdArgs {
     const StepCtl *ctl;
     int a_rows_from_ctl, rows_per_bunch;
     int kblocks;              // frames / 64
     int Kp, Np;
+    float *W, *D;             // fp32 weights and momentum of this layer, pitch Np
     bf16 *w_hi, *w_lo;        // shadows, pitch Np
     float mom, lr, Mg, wc;
 };
 struct DwUpdPlan {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;   // operands (bf16, MN-major boxes)
-    CUtensorMap w, d;                     // fp32 W and delta tiles (load + store)
     DwUpdArgs args;
     int tiles_i, tiles_j;
+    int stages;                           // operand ring depth: 1 (48 KB, up to 3 CTAs per SM) or 2
 };
 int launch_dw_update(const DwUpdPlan &p, cudaStream_t s);
 int dw_update_init();
