@@ -23,7 +23,7 @@ constexpr int STAGE = 2 * A_TILE + 2 * B_TILE; // 48 KB
 constexpr int G_PITCH = BN + 4;                // floats; 272-byte rows keep the row-per-thread float4 stores conflict-free
 constexpr int NTHREADS = 320;
 constexpr int ROWS_PER_WARP = TILE_I / 8;      // 16
-constexpr int RB = 4;                          // rows whose W / delta loads are in flight per warp
+constexpr int RB = ROWS_PER_WARP;              // ALL rows of a warp have their W / delta loads in flight during the GEMM
 static_assert(TILE_I * G_PITCH * 4 <= STAGE, "gradient staging must fit in one drained operand stage");
 template <int STAGES> constexpr int smem_bytes() { return STAGES * STAGE + 1024; }
 }  // namespace dwu
@@ -37,7 +37,7 @@ __device__ __forceinline__ float2 ld_stream_f2(const float *p)
 }
 
 template <int STAGES>
-__global__ void __launch_bounds__(dwu::NTHREADS, (STAGES == 1) ? 3 : 2)
+__global__ void __launch_bounds__(dwu::NTHREADS, 2)
 dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const DwUpdArgs g)
 {
@@ -141,41 +141,24 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
         epi_bar_sync();
         const float mom = g.mom, lr = g.lr, Mg = g.Mg, wc = g.wc;
-#pragma unroll 1
-        for (int rb = 0; rb < ROWS_PER_WARP; rb += RB) {
-            float2 wn[RB], dn[RB];
-            if (rb + RB < ROWS_PER_WARP) {        // prefetch the next row block
 #pragma unroll
-                for (int x = 0; x < RB; x++) {
-                    const int k = i0 + rbase + rb + RB + x;
-                    const size_t o = (size_t)(k < g.Kp ? k : 0) * g.Np + colo;
-                    wn[x] = ld_stream_f2(g.W + o);
-                    dn[x] = ld_stream_f2(g.D + o);
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < RB; x++) {
-                const int r = rbase + rb + x, k = i0 + r;
-                if (k < g.Kp) {
-                    const float2 gr = *reinterpret_cast<const float2 *>(Gs + (size_t)r * G_PITCH + 2 * lane);
-                    float2 dd = d[x], ww = w[x];
-                    dd.x = mom * dd.x - lr * (gr.x / Mg + wc * ww.x);
-                    dd.y = mom * dd.y - lr * (gr.y / Mg + wc * ww.y);
-                    ww.x = dd.x + ww.x;
-                    ww.y = dd.y + ww.y;
-                    const size_t o = (size_t)k * g.Np + colo;
-                    *reinterpret_cast<float2 *>(g.W + o) = ww;        // 32 lanes x 8 B = one 256-byte row segment
-                    *reinterpret_cast<float2 *>(g.D + o) = dd;
-                    bf16 h0, l0, h1, l1;
-                    split_bf16(ww.x, h0, l0);
-                    split_bf16(ww.y, h1, l1);
-                    *reinterpret_cast<uint32_t *>(g.w_hi + o) = pack_bf16x2(h0, h1);
-                    *reinterpret_cast<uint32_t *>(g.w_lo + o) = pack_bf16x2(l0, l1);
-                }
-            }
-            if (rb + RB < ROWS_PER_WARP) {
-#pragma unroll
-                for (int x = 0; x < RB; x++) { w[x] = wn[x]; d[x] = dn[x]; }
+        for (int x = 0; x < RB; x++) {
+            const int r = rbase + x, k = i0 + r;
+            if (k < g.Kp) {
+                const float2 gr = *reinterpret_cast<const float2 *>(Gs + (size_t)r * G_PITCH + 2 * lane);
+                float2 dd = d[x], ww = w[x];
+                dd.x = mom * dd.x - lr * (gr.x / Mg + wc * ww.x);
+                dd.y = mom * dd.y - lr * (gr.y / Mg + wc * ww.y);
+                ww.x = dd.x + ww.x;
+                ww.y = dd.y + ww.y;
+                const size_t o = (size_t)k * g.Np + colo;
+                *reinterpret_cast<float2 *>(g.W + o) = ww;        // 32 lanes x 8 B = one 256-byte row segment
+                *reinterpret_cast<float2 *>(g.D + o) = dd;
+                bf16 h0, l0, h1, l1;
+                split_bf16(ww.x, h0, l0);
+                split_bf16(ww.y, h1, l1);
+                *reinterpret_cast<uint32_t *>(g.w_hi + o) = pack_bf16x2(h0, h1);
+                *reinterpret_cast<uint32_t *>(g.w_lo + o) = pack_bf16x2(l0, l1);
             }
         }
     }

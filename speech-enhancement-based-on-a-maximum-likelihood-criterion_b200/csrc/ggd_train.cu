@@ -214,7 +214,7 @@ static int build_plans(ggd_handle *h)
             GGD_TRY(make_tmap_bf16(&p.a_lo, al, arows, ly.Kp, ly.Kp, 64));
             GGD_TRY(make_tmap_bf16(&p.b_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 64));
             GGD_TRY(make_tmap_bf16(&p.b_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 64));
-            p.stages = (h->Mp / 64 <= 2) ? 1 : 2;
+            p.stages = 2;
             DwUpdArgs &a = p.args;
             a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
             a.kblocks = h->Mp / 64; a.Kp = ly.Kp; a.Np = ly.Np;
