@@ -140,6 +140,8 @@ int ggd_debug_gemm(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, 
  * 4 last stage landed, 5 last MMA issued, 6 accumulator ready, 7 cluster exchange done, 8 epilogue done, 9 exit) */
 int ggd_debug_gemm_timed(int a_mn, int b_mn, int I, int J, int R, int bn, int splits, const float *A, const float *B, float *D,
                          int reps, float *avg_ms, unsigned long long *trace_host, int trace_ctas);
+/* one traced training step (tuning aid): see csrc/ggd_train.cu */
+int ggd_debug_trace_step(ggd_handle *h, const float *in, const float *targ, int fused, float *out, int max_launches, int *n_launches);
 /* writes a 128-byte ncclUniqueId (rank 0 creates it, every rank passes it in ggd_config) */
 int ggd_nccl_unique_id(void *out128);
 

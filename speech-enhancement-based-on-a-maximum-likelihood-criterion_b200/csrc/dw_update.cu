@@ -28,6 +28,14 @@ static_assert(TILE_I * G_PITCH * 4 <= STAGE, "gradient staging must fit in one d
 template <int STAGES> constexpr int smem_bytes() { return STAGES * STAGE + 1024; }
 }  // namespace dwu
 
+__device__ __forceinline__ void dstamp(const DwUpdArgs &g, int slot)
+{
+    if (g.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g.trace[(size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 16 + slot] = t;
+    }
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ float2 ld_stream_f2(const float *p)
 {
@@ -52,6 +60,7 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int j0 = blockIdx.x * BN, i0 = blockIdx.y * TILE_I;
     const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
     const int nkb = g.kblocks;
+    if (threadIdx.x == 0) dstamp(g, 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
@@ -69,6 +78,7 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x == 0) dstamp(g, 1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -95,6 +105,8 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                if (it == 0) dstamp(g, 3);
+                if (it == nkb - 1) dstamp(g, 4);
                 const uint32_t a_hi = smem_u32(ring + s * STAGE), a_lo = a_hi + A_TILE;
                 const uint32_t b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
@@ -127,8 +139,10 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             w[x] = ld_stream_f2(g.W + o);
             d[x] = ld_stream_f2(g.D + o);
         }
+        if (threadIdx.x == 64) dstamp(g, 2);
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) dstamp(g, 6);
         // gradient tile -> padded shared memory (all MMAs have retired: the operand ring is free)
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + half * 32;
         float *grow = Gs + (size_t)row * G_PITCH + half * 32;
@@ -140,6 +154,7 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             for (int x = 0; x < 4; x++) *reinterpret_cast<float4 *>(grow + c + 4 * x) = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
         }
         epi_bar_sync();
+        if (threadIdx.x == 64) dstamp(g, 7);
         const float mom = g.mom, lr = g.lr, Mg = g.Mg, wc = g.wc;
 #pragma unroll
         for (int x = 0; x < RB; x++) {
@@ -162,9 +177,11 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             }
         }
     }
+    if (threadIdx.x == 64) dstamp(g, 8);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<BN>(tmem);
+    if (threadIdx.x == 0) dstamp(g, 9);
 }
 
 int launch_dw_update(const DwUpdPlan &p, cudaStream_t s)

@@ -71,6 +71,7 @@ struct DwUpdArgs {
     float *W, *D;             // fp32 weights and momentum of this layer, pitch Np
     bf16 *w_hi, *w_lo;        // shadows, pitch Np
     float mom, lr, Mg, wc;
+    unsigned long long *trace;   // optional [ctas][16] globaltimer stamps
 };
 struct DwUpdPlan {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;   // operands (bf16, MN-major boxes)

@@ -16,6 +16,7 @@
 #include <math.h>
 #include <vector>
 #include <map>
+#include <algorithm>
 
 namespace ggd {
 static thread_local char g_err[1024] = "";
@@ -820,6 +821,73 @@ int ggd_profile_kernels(ggd_handle *h, int n_frames, const float *d_in, const fl
     out->steps = nb;
     out->param_elems = (long long)h->arena;
     return rc;
+}
+
+// One training step with per-CTA phase stamps in every tensor-core kernel (tests / tuning only).
+// out[launch][12]: kind (0 fwd, 2 dx, 3 dw, 9 dw_update), ctas, first entry (us since the first kernel), last exit,
+// then medians of slots 1,2,3,4,6,7,8,9 relative to the CTA's own entry.
+int ggd_debug_trace_step(ggd_handle *h, const float *in, const float *targ, int fused, float *out, int max_launches, int *n_launches)
+{
+    if (!h || !in || !targ || !out || !n_launches || !h->tensor) { set_error("ggd_debug_trace_step: bad argument"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, h->M));
+    const int D = h->units[h->L - 1], L = h->L;
+    struct Item { int kind; int ctas; unsigned long long **slot; };
+    std::vector<Item> items;
+    for (int l = 1; l < L; l++) items.push_back({0, h->fwd[l].splits * h->fwd[l].tiles_i * h->fwd[l].tiles_j, &h->fwd[l].args.trace});
+    for (int l = L - 1; l > 0; l--) {
+        if (l != 1) items.push_back({2, h->dxp[l].splits * h->dxp[l].tiles_i * h->dxp[l].tiles_j, &h->dxp[l].args.trace});
+        if (fused && h->fused) items.push_back({9, h->dwu[l].tiles_i * h->dwu[l].tiles_j, &h->dwu[l].args.trace});
+        else items.push_back({3, h->dwp[l].tiles_i * h->dwp[l].tiles_j, &h->dwp[l].args.trace});
+    }
+    size_t total = 0;
+    for (auto &it : items) total += (size_t)it.ctas * 16;
+    unsigned long long *dbuf = nullptr;
+    GGD_CUDA(cudaMalloc(&dbuf, total * 8));
+    GGD_CUDA(cudaMemset(dbuf, 0, total * 8));
+    GGD_CUDA(cudaMemcpyAsync(h->c_in, in, (size_t)h->M * h->units[0] * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->c_targ, targ, (size_t)h->M * D * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    launch_split_rows(h->c_in, h->M, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main);
+    int launches = 0, rc = GGD_OK;
+    for (int rep = 0; rep < 3 && rc == GGD_OK; rep++) {     // two warm steps, then the traced one
+        GGD_TRY(set_ctl(h, h->c_in, h->c_targ));
+        if (rep == 2) { size_t off = 0; for (auto &it : items) { *it.slot = dbuf + off; off += (size_t)it.ctas * 16; } }
+        rc = enqueue_step(h, h->s_main, true, &launches, fused != 0);
+    }
+    cudaStreamSynchronize(h->s_main);
+    for (auto &it : items) *it.slot = nullptr;
+    std::vector<unsigned long long> hb(total);
+    cudaMemcpy(hb.data(), dbuf, total * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dbuf);
+    if (rc != GGD_OK) return rc;
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < total; i += 16) if (hb[i] && hb[i] < t0) t0 = hb[i];
+    size_t off = 0;
+    int n = 0;
+    for (auto &it : items) {
+        if (n >= max_launches) break;
+        float *o = out + (size_t)n * 12;
+        unsigned long long first = ~0ull, last = 0;
+        const int slots[8] = {1, 2, 3, 4, 6, 7, 8, 9};
+        std::vector<double> med[8];
+        for (int c = 0; c < it.ctas; c++) {
+            const unsigned long long *t = &hb[off + (size_t)c * 16];
+            if (!t[0]) continue;
+            if (t[0] < first) first = t[0];
+            if (t[9] > last) last = t[9];
+            for (int k = 0; k < 8; k++) if (t[slots[k]]) med[k].push_back((double)(t[slots[k]] - t[0]) / 1000.0);
+        }
+        o[0] = (float)it.kind; o[1] = (float)it.ctas; o[2] = (float)((double)(first - t0) / 1000.0); o[3] = (float)((double)(last - t0) / 1000.0);
+        for (int k = 0; k < 8; k++) {
+            if (med[k].empty()) { o[4 + k] = -1; continue; }
+            std::sort(med[k].begin(), med[k].end());
+            o[4 + k] = (float)med[k][med[k].size() / 2];
+        }
+        off += (size_t)it.ctas * 16;
+        n++;
+    }
+    *n_launches = n;
+    return GGD_OK;
 }
 
 int ggd_nccl_unique_id(void *out128)
