@@ -67,6 +67,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// ---- PTX: programmatic dependent launch (the next kernel of the stream may start its prologue early) ----
+// pdl_wait: block until every kernel this launch depends on has completed and its writes are visible.
+// pdl_trigger: allow the dependent kernel to be scheduled (it still blocks in its own pdl_wait until we exit).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- PTX: TMA (cp.async.bulk.tensor) --------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");

@@ -58,7 +58,6 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j0 = blockIdx.x * BN, i0 = blockIdx.y * TILE_I;
-    const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
     const int nkb = g.kblocks;
     if (threadIdx.x == 0) dstamp(g, 0);
 
@@ -78,6 +77,8 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    pdl_wait();      // prologue overlapped the previous kernel's tail; its outputs are visible from here on
+    const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
     if (threadIdx.x == 0) dstamp(g, 1);
 
     if (warp == 0) {
@@ -154,6 +155,7 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             for (int x = 0; x < 4; x++) *reinterpret_cast<float4 *>(grow + c + 4 * x) = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
         }
         epi_bar_sync();
+        pdl_trigger();
         if (threadIdx.x == 64) dstamp(g, 7);
         const float mom = g.mom, lr = g.lr, Mg = g.Mg, wc = g.wc;
 #pragma unroll
@@ -190,6 +192,10 @@ int launch_dw_update(const DwUpdPlan &p, cudaStream_t s)
     cfg.gridDim = dim3(p.tiles_j, p.tiles_i, 1);
     cfg.blockDim = dim3(dwu::NTHREADS);
     cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
     if (p.stages == 1) {
         cfg.dynamicSmemBytes = dwu::smem_bytes<1>();
         GGD_CUDA(cudaLaunchKernelEx(&cfg, dw_update_kernel<1>, p.a_hi, p.a_lo, p.b_hi, p.b_lo, p.args));

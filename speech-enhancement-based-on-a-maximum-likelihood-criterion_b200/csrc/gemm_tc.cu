@@ -77,7 +77,7 @@ __device__ __forceinline__ void epilogue16(const GemmArgs &g, int i, int j, floa
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 const float x = v[e] + __ldg(g.bias + j + e);
-                r[e] = (row_ok && j + e < g.J) ? 1.0f / (1.0f + expf(-x)) : 0.0f;   // kernSigmoid, DevFunc.cu:36-51
+                r[e] = (row_ok && j + e < g.J) ? __fdividef(1.0f, 1.0f + __expf(-x)) : 0.0f;   // kernSigmoid, DevFunc.cu:36-51 (rel. error ~2e-7)
             }
         } else {  // EPI_DX_DSIGMOID
             const uint4 *yh = reinterpret_cast<const uint4 *>(g.y_hi + (size_t)i * g.ldy + j);
@@ -131,7 +131,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int j0 = blockIdx.y * BN, i0 = blockIdx.z * TILE_I;
     const int kb0 = (g.kblocks * rank) / S, kb1 = (g.kblocks * (rank + 1)) / S;
     const int nkb = kb1 - kb0;
-    const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
     if (threadIdx.x == 0) stamp(g, 0);
 
     if (warp == 0 && lane == 0) {
@@ -151,6 +150,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    // everything above overlapped the tail of the previous kernel (PDL); from here on we read what it produced
+    pdl_wait();
+    const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
     if (threadIdx.x == 0) stamp(g, 1);
 
     if (warp == 0) {
@@ -223,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         tc_fence_after();
         if (threadIdx.x == 64) stamp(g, 6);
     }
+    pdl_trigger();   // mainloop done on this CTA: the next kernel may be scheduled as SMs drain
 
     const int q = warp & 3;                 // TMEM lane quadrant of this warp
     const int row = q * 32 + lane;          // output row inside the tile
@@ -317,10 +320,12 @@ static int launch_inst(const GemmPlan &p, cudaStream_t s)
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = TileCfg<BN>::SMEM;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = p.splits; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
     GGD_CUDA(cudaLaunchKernelEx(&cfg, kern, p.a_hi, p.a_lo, p.b_hi, p.b_lo, p.args));
     return GGD_OK;
 }

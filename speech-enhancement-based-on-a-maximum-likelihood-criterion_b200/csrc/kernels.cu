@@ -41,17 +41,19 @@ void launch_split_rows(const float *src, int rows, int cols, bf16 *hi, bf16 *lo,
 }
 
 // ------------------------------------------------------------------------------------------------
-// |e|^p with the cheap exact cases of the two named configurations (beta = 2, beta = 1)
+// |e|^p: exact for the two named configurations (beta = 2, beta = 1); otherwise exp2(p*log2 a) with the hardware
+// approximations (relative error ~1e-6 * p*|log2 a|, far inside the 1e-3 tolerance; the reference uses powf).
 __device__ __forceinline__ float pow_abs(float a, float p)
 {
     if (p == 2.0f) return a * a;
     if (p == 1.0f) return a;
     if (p == 0.0f) return 1.0f;
-    return powf(a, p);
+    return (a > 0.0f) ? exp2f(p * __log2f(a)) : 0.0f;
 }
 
 constexpr int LOSS_COLS = 32;   // columns per block (one warp-wide coalesced row segment)
-constexpr int LOSS_ROWL = 32;   // row lanes per block (1024 threads: at M = 128 each thread owns 4 rows per column)
+constexpr int LOSS_ROWL = 32;   // row lanes per block (1024 threads)
+constexpr int LOSS_RMAX = 8;    // errors kept in registers per thread (bunches up to 256 frames make one pass over memory)
 
 __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
 {
@@ -63,29 +65,46 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
     const float *targ = a.ctl->targ + (size_t)bunch * a.M * a.D;
     const bool live = d < a.D;
     const float beta = a.beta;
+    const bool in_regs = a.M <= LOSS_ROWL * LOSS_RMAX;
+    float er[LOSS_RMAX];
 
-    // pass 1: s_d = sum_m |e_md|^beta  (DevSumcol of Devindex2 of Devabsolutevalus of Deverror)
-    if (a.mode != 2) {
+    // pass 1: e = out - targ;  s_d = sum_m |e_md|^beta  (Deverror, Devabsolutevalus, Devindex2, DevSumcol)
+    {
         float s = 0.0f;
-        if (live)
-            for (int m = ty; m < a.M; m += LOSS_ROWL) {
-                const float e = a.out[(size_t)m * a.ldo + d] - __ldg(targ + (size_t)m * a.D + d);
-                s += pow_abs(fabsf(e), beta);
-            }
-        red[ty][tx] = s;
-        __syncthreads();
-        if (ty == 0) {
-            float t = red[0][tx];
+        if (live) {
+            if (in_regs) {
 #pragma unroll
-            for (int r = 1; r < LOSS_ROWL; r++) t += red[r][tx];
-            s_col[tx] = t;
-            if (live && a.mode == 1) a.colsum[d] = t;
+                for (int i = 0; i < LOSS_RMAX; i++) {
+                    const int m = ty + i * LOSS_ROWL;
+                    er[i] = (m < a.M) ? a.out[(size_t)m * a.ldo + d] - __ldg(targ + (size_t)m * a.D + d) : 0.0f;
+                }
+                if (a.mode != 2) {
+#pragma unroll
+                    for (int i = 0; i < LOSS_RMAX; i++) s += pow_abs(fabsf(er[i]), beta);
+                }
+            } else if (a.mode != 2) {
+                for (int m = ty; m < a.M; m += LOSS_ROWL) {
+                    const float e = a.out[(size_t)m * a.ldo + d] - __ldg(targ + (size_t)m * a.D + d);
+                    s += pow_abs(fabsf(e), beta);
+                }
+            }
         }
-        __syncthreads();
-        if (a.mode == 1) return;
-    } else {
-        if (ty == 0) s_col[tx] = live ? a.colsum[d] : 0.0f;
-        __syncthreads();
+        if (a.mode != 2) {
+            red[ty][tx] = s;
+            __syncthreads();
+            if (ty == 0) {
+                float t = red[0][tx];
+#pragma unroll
+                for (int r = 1; r < LOSS_ROWL; r++) t += red[r][tx];
+                s_col[tx] = t;
+                if (live && a.mode == 1) a.colsum[d] = t;
+            }
+            __syncthreads();
+            if (a.mode == 1) return;
+        } else {
+            if (ty == 0) s_col[tx] = live ? a.colsum[d] : 0.0f;
+            __syncthreads();
+        }
     }
 
     // alpha_d = (beta * s_d / Mg)^(1/beta)   (DevDivide, DevVecMulNum, Devindex2; BP_GPU.cu:417-420)
@@ -98,7 +117,7 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
                 const float v2 = v1 * beta;
                 const float al = powf(v2, 1.0f / beta);
                 a.alpha[d] = al;
-                pa = pow_abs(al, beta);
+                pa = (beta == 2.0f) ? al * al : ((beta == 1.0f) ? al : powf(al, beta));
                 contrib = logf(al) + s / ((float)a.Mg * pa);   // ln alpha_d + sum_m (|e|/alpha_d)^beta / M
             } else {
                 contrib = s / (float)a.Mg;                      // E_beta = sum |e|^beta / M
@@ -117,15 +136,11 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
     //         (DevSubClean2 + DevVecMulNum, or Devfunc2 + DevVecMulNum when MLflag == 1); exactly 0 at e == 0
     if (!live) return;
     const float invM = 1.0f / a.Mg;
-    const float pa = s_pa[tx];
-    for (int m = ty; m < a.M; m += LOSS_ROWL) {
-        const float e = a.out[(size_t)m * a.ldo + d] - __ldg(targ + (size_t)m * a.D + d);
-        float r;
-        if (e == 0.0f) {
-            r = 0.0f;
-        } else {
-            const float p = pow_abs(fabsf(e), beta - 1.0f);
-            r = a.ml ? (p * beta / pa) : (beta * p);
+    const float scale = a.ml ? beta / s_pa[tx] : beta;
+    auto emit = [&](int m, float e) {
+        float r = 0.0f;
+        if (e != 0.0f) {
+            r = pow_abs(fabsf(e), beta - 1.0f) * scale;
             r = (e > 0.0f) ? r : -r;
         }
         r *= invM;
@@ -137,6 +152,15 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
             a.dx_hi[o] = h;
             a.dx_lo[o] = l;
         }
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < LOSS_RMAX; i++) {
+            const int m = ty + i * LOSS_ROWL;
+            if (m < a.M) emit(m, er[i]);
+        }
+    } else {
+        for (int m = ty; m < a.M; m += LOSS_ROWL) emit(m, a.out[(size_t)m * a.ldo + d] - __ldg(targ + (size_t)m * a.D + d));
     }
 }
 
