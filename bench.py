@@ -84,6 +84,49 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bench_lps(pkg, torch, dev, peaks, with_cpu):
+    """LPS extraction: 10 minutes of int16 noise clip(round(N(0, 3000^2))), device-resident and e2e."""
+    n = 16000 * 600
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    pcm = torch.clamp(torch.round(torch.randn(n, device=dev, generator=g) * 3000.0), -32768, 32767).to(torch.int16)
+    ex = pkg.Wav2LPS(dev.index or 0)
+    nf = pkg.lps_nframes(n)
+    out = torch.empty(nf, 257, device=dev, dtype=torch.float32)
+    off = [0, n]
+    for _ in range(3):
+        ex.extract_batch_device(pcm.data_ptr(), off, out.data_ptr())
+    ms = []
+    for _ in range(10):
+        ex.extract_batch_device(pcm.data_ptr(), off, out.data_ptr())
+        ms.append(ex.last_kernel_ms())
+    kms = float(np.median(ms))
+    res = {"frames": nf, "value": nf / (kms * 1e-3), "unit": "frames/s", "kernel_ms": kms,
+           "roofline": {"bound": "hbm", "achieved": 1540.0 * nf / (kms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": 1540.0 * nf / (kms * 1e-3) / 1e9 / peaks["hbm"],
+                        "note": "256 int16 in + 257 fp32 out per frame; the kernel is instruction/shared-memory bound (split-radix FFT + double log)"}}
+    h = pcm.cpu().numpy()
+    t0 = time.perf_counter()
+    feats = ex.extract(h)
+    dt = time.perf_counter() - t0
+    res["e2e"] = {"value": nf / dt, "unit": "frames/s", "h2d_bytes": int(h.nbytes), "d2h_bytes": int(feats.nbytes)}
+    if with_cpu:
+        try:
+            from oracle import oracle as O, refcuda
+            sample = h[:16000 * 60]
+            if refcuda.available("Wav2LPS_be_ref"):
+                _, dtc = refcuda.ref_wav2lps(sample)
+                kind = "reference"
+            else:
+                t0 = time.perf_counter(); O.lps_extract(sample); dtc = time.perf_counter() - t0
+                kind = "port"
+            res["cpu_baseline"] = {"value": pkg.lps_nframes(len(sample)) / dtc, "unit": "frames/s", "cores": 1, "kind": kind,
+                                   "sample": "60 s of the same noise through %s (one process, incl. file I/O)" % ("oracle/_ref/Wav2LPS_be_ref (-O2)" if kind == "reference" else "oracle/lps_oracle.c")}
+        except Exception as ex2:
+            res["cpu_baseline"] = {"unavailable": str(ex2)[:200]}
+    ex.close()
+    return res
+
+
 def make_net_inputs(ls, seed=1):
     from oracle import oracle as O
     return O.init_weights(ls, seed=seed, beta=2.0)
@@ -133,6 +176,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lps", action="store_true")
     args = ap.parse_args()
     ls, ml, beta, bunch = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,6 +310,33 @@ def main():
         cpu = {"value": n * bunch / dtc, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                "sample": "%d bunches of %d frames through oracle/ggd_oracle.c (OpenMP)" % (n, bunch)}
 
+    # ---- the reference's own CUDA trainer (BP_GPU.cu + DevFunc.cu + cuBLAS, built unmodified into oracle/_ref) on the
+    #      same GPU, same shapes: reported next to ours, not the optimisation target
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refcuda
+            if refcuda.available("libref_bpgpu.so"):
+                nref = 200 * bunch
+                xr = d_in[:nref].cpu().numpy(); tr = d_tg[:nref].cpu().numpy()
+                ref = refcuda.RefBPGPU(ls, bunch, LR, MOM, WC, beta, ml, W, b, gpu=local_rank)
+                ref.train(xr[:8 * bunch], tr[:8 * bunch])
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ref.train(xr, tr)
+                torch.cuda.synchronize()
+                dtr = time.perf_counter() - t0
+                ref.close()
+                ref_cuda = {"value": nref / dtr, "unit": "frames/s", "ms_per_step": 1e3 * dtr / 200,
+                            "what": "reference BP_GPU::train (fp32 cuBLAS SGEMM, 53 launches/bunch), 200 bunches incl. its H2D copy"}
+        except Exception as ex:     # the baseline is optional; never let it break the measurement
+            ref_cuda = {"unavailable": str(ex)[:200]}
+
+    # ---- LPS front end (second half of the metric): frames/s of the extraction kernel on synthetic 16 kHz noise
+    lps = None
+    if rank == 0 and not args.no_lps:
+        lps = bench_lps(pkg, torch, dev, peaks, world == 1 and not args.no_cpu_baseline)
+
     if rank == 0:
         line = {"metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -275,7 +346,7 @@ def main():
                            "global_minibatch": bunch * world, "l2": "inputs (737 MB/chunk) and weight state (250 MB) exceed the 126 MB L2",
                            "parallelism": "dp%d (frame-sharded; allreduce of sum|e|^beta and of the gradients)" % world},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "kernels": kern, "flops_per_frame": fpf,
+                "kernels": kern, "flops_per_frame": fpf, "reference_cuda": ref_cuda, "lps": lps,
                 "tensor_frac_whole_step": (fpf * bunch * K / (ms * 1e-3) / 1e12) / peaks["bf16_sus"]}
         print(json.dumps(line), flush=True)
     net.close()

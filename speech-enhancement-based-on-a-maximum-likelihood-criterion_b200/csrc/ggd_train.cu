@@ -49,6 +49,7 @@ struct LayerInfo {
     int prev, cur;      // real units
     int Kp, Np;         // padded units (multiples of 64)
     size_t w_off, b_off;  // element offsets in the parameter arenas
+    size_t gb_off;        // offset of the bias gradient in G (packed after the arena so that one allreduce covers all biases)
 };
 
 struct ggd_handle {
@@ -74,8 +75,10 @@ struct ggd_handle {
     bf16 *c_hi, *c_lo;
     size_t cap;         // frames
     std::map<const void *, size_t> pinned;
-    cudaStream_t s_main;
+    cudaStream_t s_main, s_comm;
     cudaEvent_t ev0, ev1, ev2;
+    cudaEvent_t ev_dw[GGD_MAXLAYER], ev_bias, ev_done;   // fork/join between the compute and the communication stream
+    size_t nbias;       // packed bias-gradient elements
     // plans + graphs
     GemmPlan fwd[GGD_MAXLAYER], dxp[GGD_MAXLAYER], dwp[GGD_MAXLAYER];
     DwUpdPlan dwu[GGD_MAXLAYER];
@@ -308,6 +311,20 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             launch_simt_gemm(h->y32[l - 1], 1, ly.Kp, h->dx32[l], 1, ly.Np, h->G + ly.w_off, ly.Np, ly.prev, ly.cur, h->M, s);
             (*launches)++;
         }
+        if (h->has_comm && apply_update) {
+            // this layer's weight gradient is complete: allreduce it and apply the update on the communication stream
+            // while the compute stream continues with the layers below
+            GGD_CUDA(cudaEventRecord(h->ev_dw[l], s));
+            GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_dw[l], 0));
+            { ProfScope ps(h, KC_ALLREDUCE, h->s_comm);
+              GGD_NCCL(ncclAllReduce(h->G + ly.w_off, h->G + ly.w_off, (size_t)ly.Kp * ly.Np, ncclFloat, ncclSum, h->comm, h->s_comm)); (*launches)++; }
+            UpdArgs ua;
+            memset(&ua, 0, sizeof ua);
+            ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
+            ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
+            ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
+            { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_update(ua, h->sm_count / 2, h->s_comm); (*launches)++; }
+        }
     }
     {
         ProfScope ps(h, KC_BIAS, s);
@@ -319,7 +336,7 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             BiasGradLayer &b = ba.layer[ba.nlayers++];
             b.dx32 = h->tensor ? nullptr : h->dx32[l];
             b.hi = h->tensor ? h->dx_hi[l] : nullptr; b.lo = h->tensor ? h->dx_lo[l] : nullptr;
-            b.ld = ly.Np; b.N = ly.cur; b.dst = h->G + ly.b_off;
+            b.ld = ly.Np; b.N = ly.cur; b.dst = h->G + ly.gb_off;
             b.b = h->P + ly.b_off; b.db = h->Dl + ly.b_off;
         }
         if (fused) {   // biases are updated right here and this is the last kernel of the step
@@ -328,22 +345,39 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         launch_bias_grad(ba, s); (*launches)++;
     }
     if (fused) { GGD_CUDA(cudaGetLastError()); return GGD_OK; }
-    if (h->has_comm) {
-        // frame-sharded data parallelism: sum the weight and bias gradients of all ranks
-        ProfScope ps(h, KC_ALLREDUCE, s);
-        GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena, ncclFloat, ncclSum, h->comm, s));
-        (*launches)++;
-    }
-    if (apply_update) {
-        UpdArgs ua;
+    auto make_upd = [&](UpdArgs &ua) {
         memset(&ua, 0, sizeof ua);
-        for (int l = 1; l < L; l++) {
-            const LayerInfo &ly = h->lay[l];
-            ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
-            ua.seg[ua.nseg++] = {(long long)ly.b_off, (long long)ly.Np, 0.0f, 0};   // no decay on biases (BP_GPU.cu:435)
-        }
         ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
         ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
+    };
+    if (h->has_comm && apply_update) {
+        // Frame-sharded data parallelism: the weight gradients were allreduced and applied layer by
+        // layer on the communication stream while the backward pass went on (see the loop above); what is left is
+        // the packed bias gradients, the bias update, the bunch counter, and the join.
+        GGD_CUDA(cudaEventRecord(h->ev_bias, s));
+        GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_bias, 0));
+        { ProfScope ps(h, KC_ALLREDUCE, h->s_comm);
+          GGD_NCCL(ncclAllReduce(h->G + h->arena, h->G + h->arena, h->nbias, ncclFloat, ncclSum, h->comm, h->s_comm)); (*launches)++; }
+        UpdArgs ua;
+        make_upd(ua);
+        for (int l = 1; l < L; l++) ua.seg[ua.nseg++] = {(long long)h->lay[l].b_off, (long long)h->lay[l].gb_off, (long long)h->lay[l].Np, 0.0f, 0};
+        ua.ctl = h->ctl;
+        { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_update(ua, 8, h->s_comm); (*launches)++; }
+        GGD_CUDA(cudaEventRecord(h->ev_done, h->s_comm));
+        GGD_CUDA(cudaStreamWaitEvent(s, h->ev_done, 0));
+    } else if (h->has_comm) {
+        ProfScope ps(h, KC_ALLREDUCE, s);
+        GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena + h->nbias, ncclFloat, ncclSum, h->comm, s));
+        (*launches)++;
+        { ProfScope ps2(h, KC_ADVANCE, s); launch_advance(h->ctl, s); (*launches)++; }
+    } else if (apply_update) {
+        UpdArgs ua;
+        make_upd(ua);
+        for (int l = 1; l < L; l++) {
+            const LayerInfo &ly = h->lay[l];
+            ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
+            ua.seg[ua.nseg++] = {(long long)ly.b_off, (long long)ly.gb_off, (long long)ly.Np, 0.0f, 0};   // no decay on biases (BP_GPU.cu:435)
+        }
         ua.ctl = h->ctl;   // the update kernel also advances the bunch counter
         ProfScope ps(h, KC_UPDATE, s);
         launch_update(ua, h->sm_count, s); (*launches)++;
@@ -467,13 +501,18 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         ly.b_off = off; off += ly.Np;
     }
     h->arena = off;
+    h->nbias = 0;
+    for (int l = 1; l < h->L; l++) { h->lay[l].gb_off = off + h->nbias; h->nbias += h->lay[l].Np; }
     auto fail = [&](int rc) { ggd_destroy(h); return rc; };
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s -> %s", #expr, cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? GGD_ENOMEM : GGD_ECUDA); } } while (0)
     CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+    for (int l = 0; l < GGD_MAXLAYER; l++) CK(cudaEventCreateWithFlags(&h->ev_dw[l], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_bias, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev2));
-    CK(cudaMalloc(&h->P, off * sizeof(float))); CK(cudaMalloc(&h->Dl, off * sizeof(float))); CK(cudaMalloc(&h->G, off * sizeof(float)));
+    CK(cudaMalloc(&h->P, off * sizeof(float))); CK(cudaMalloc(&h->Dl, off * sizeof(float))); CK(cudaMalloc(&h->G, (off + h->nbias) * sizeof(float)));
     CK(cudaMalloc(&h->Phi, off * sizeof(bf16))); CK(cudaMalloc(&h->Plo, off * sizeof(bf16)));
-    CK(cudaMemset(h->P, 0, off * sizeof(float))); CK(cudaMemset(h->Dl, 0, off * sizeof(float))); CK(cudaMemset(h->G, 0, off * sizeof(float)));
+    CK(cudaMemset(h->P, 0, off * sizeof(float))); CK(cudaMemset(h->Dl, 0, off * sizeof(float))); CK(cudaMemset(h->G, 0, (off + h->nbias) * sizeof(float)));
     CK(cudaMemset(h->Phi, 0, off * sizeof(bf16))); CK(cudaMemset(h->Plo, 0, off * sizeof(bf16)));
     for (int l = 0; l < h->L; l++) {
         const size_t n = (size_t)h->Mp * h->upad[l];
@@ -537,6 +576,10 @@ int ggd_destroy(ggd_handle *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
+    for (int l = 0; l < GGD_MAXLAYER; l++) if (h->ev_dw[l]) cudaEventDestroy(h->ev_dw[l]);
+    if (h->ev_bias) cudaEventDestroy(h->ev_bias);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->s_comm) cudaStreamDestroy(h->s_comm);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     delete h;
     return GGD_OK;
@@ -787,7 +830,7 @@ int ggd_debug_read(ggd_handle *h, int what, int layer, float *dst)
         GGD_CUDA(cudaMemcpy2D(dst, ly.cur * sizeof(float), h->G + ly.w_off, ly.Np * sizeof(float), ly.cur * sizeof(float), ly.prev, cudaMemcpyDeviceToHost));
         return GGD_OK;
     case 4:
-        GGD_CUDA(cudaMemcpy(dst, h->G + ly.b_off, ly.cur * sizeof(float), cudaMemcpyDeviceToHost));
+        GGD_CUDA(cudaMemcpy(dst, h->G + ly.gb_off, ly.cur * sizeof(float), cudaMemcpyDeviceToHost));
         return GGD_OK;
     }
     set_error("ggd_debug_read: unknown selector %d", what);

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdArgs a)
     const long long n4 = sg.n >> 2;
     float4 *P = reinterpret_cast<float4 *>(a.P + sg.off);
     float4 *D = reinterpret_cast<float4 *>(a.Dl + sg.off);
-    const float4 *G = reinterpret_cast<const float4 *>(a.G + sg.off);
+    const float4 *G = reinterpret_cast<const float4 *>(a.G + sg.goff);
     uint2 *Hi = reinterpret_cast<uint2 *>(a.Phi + sg.off);
     uint2 *Lo = reinterpret_cast<uint2 *>(a.Plo + sg.off);
     const float mom = a.mom, lr = a.lr, Mg = a.Mg, wc = sg.wc;

@@ -58,6 +58,7 @@ void launch_bias_grad(const BiasGradArgs &a, cudaStream_t s);
 
 struct UpdSeg {
     long long off;   // element offset in the parameter arena (multiple of 4)
+    long long goff;  // element offset of the matching gradients in G
     long long n;     // elements (multiple of 4)
     float wc;        // weight cost (0 for biases)
     int shadow;      // write bf16 hi/lo shadows
