@@ -114,7 +114,8 @@ def bench_lps(pkg, torch, dev, peaks, with_cpu):
             from oracle import oracle as O, refcuda
             sample = h[:16000 * 60]
             if refcuda.available("Wav2LPS_be_ref"):
-                _, dtc = refcuda.ref_wav2lps(sample)
+                with quiet_stdout():
+                    _, dtc = refcuda.ref_wav2lps(sample)
                 kind = "reference"
             else:
                 t0 = time.perf_counter(); O.lps_extract(sample); dtc = time.perf_counter() - t0
@@ -125,6 +126,20 @@ def bench_lps(pkg, torch, dev, peaks, with_cpu):
             res["cpu_baseline"] = {"unavailable": str(ex2)[:200]}
     ex.close()
     return res
+
+
+class quiet_stdout:
+    """Redirects the C-level stdout (the reference library printf()s) so that the JSON line stays the only output."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null); os.close(self.saved)
 
 
 def make_net_inputs(ls, seed=1):
@@ -319,14 +334,15 @@ def main():
             if refcuda.available("libref_bpgpu.so"):
                 nref = 200 * bunch
                 xr = d_in[:nref].cpu().numpy(); tr = d_tg[:nref].cpu().numpy()
-                ref = refcuda.RefBPGPU(ls, bunch, LR, MOM, WC, beta, ml, W, b, gpu=local_rank)
-                ref.train(xr[:8 * bunch], tr[:8 * bunch])
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                ref.train(xr, tr)
-                torch.cuda.synchronize()
-                dtr = time.perf_counter() - t0
-                ref.close()
+                with quiet_stdout():
+                    ref = refcuda.RefBPGPU(ls, bunch, LR, MOM, WC, beta, ml, W, b, gpu=local_rank)
+                    ref.train(xr[:8 * bunch], tr[:8 * bunch])
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    ref.train(xr, tr)
+                    torch.cuda.synchronize()
+                    dtr = time.perf_counter() - t0
+                    ref.close()
                 ref_cuda = {"value": nref / dtr, "unit": "frames/s", "ms_per_step": 1e3 * dtr / 200,
                             "what": "reference BP_GPU::train (fp32 cuBLAS SGEMM, 53 launches/bunch), 200 bunches incl. its H2D copy"}
         except Exception as ex:     # the baseline is optional; never let it break the measurement

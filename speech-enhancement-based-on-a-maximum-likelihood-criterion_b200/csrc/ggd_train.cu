@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include <nccl.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <vector>
@@ -89,6 +90,7 @@ struct ggd_handle {
     // DP
     ncclComm_t comm;
     bool has_comm;
+    int dp_overlap;     // 1: per-layer allreduce + update on the communication stream (default); 0: one allreduce at the end
     // host mirrors / stats
     std::vector<float> losses;
     std::vector<float> h_out;
@@ -311,7 +313,7 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             launch_simt_gemm(h->y32[l - 1], 1, ly.Kp, h->dx32[l], 1, ly.Np, h->G + ly.w_off, ly.Np, ly.prev, ly.cur, h->M, s);
             (*launches)++;
         }
-        if (h->has_comm && apply_update) {
+        if (h->has_comm && apply_update && h->dp_overlap) {
             // this layer's weight gradient is complete: allreduce it and apply the update on the communication stream
             // while the compute stream continues with the layers below
             GGD_CUDA(cudaEventRecord(h->ev_dw[l], s));
@@ -350,7 +352,21 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
         ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
     };
-    if (h->has_comm && apply_update) {
+    if (h->has_comm && apply_update && !h->dp_overlap) {
+        // one allreduce of the whole gradient arena, then the flat update (no overlap; GGD_DP_OVERLAP=0)
+        { ProfScope ps(h, KC_ALLREDUCE, s);
+          GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena + h->nbias, ncclFloat, ncclSum, h->comm, s)); (*launches)++; }
+        UpdArgs ua;
+        make_upd(ua);
+        for (int l = 1; l < L; l++) {
+            const LayerInfo &ly = h->lay[l];
+            ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
+            ua.seg[ua.nseg++] = {(long long)ly.b_off, (long long)ly.gb_off, (long long)ly.Np, 0.0f, 0};
+        }
+        ua.ctl = h->ctl;
+        ProfScope ps(h, KC_UPDATE, s);
+        launch_update(ua, h->sm_count, s); (*launches)++;
+    } else if (h->has_comm && apply_update) {
         // Frame-sharded data parallelism: the weight gradients were allreduced and applied layer by
         // layer on the communication stream while the backward pass went on (see the loop above); what is left is
         // the packed bias gradients, the bias update, the bunch counter, and the join.
@@ -506,7 +522,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     auto fail = [&](int rc) { ggd_destroy(h); return rc; };
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s -> %s", #expr, cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? GGD_ENOMEM : GGD_ECUDA); } } while (0)
     CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->s_comm, cudaStreamNonBlocking));
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); CK(cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi)); }
     for (int l = 0; l < GGD_MAXLAYER; l++) CK(cudaEventCreateWithFlags(&h->ev_dw[l], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_bias, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev2));
@@ -550,9 +566,16 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         if (!cfg->nccl_unique_id) { set_error("world_size > 1 needs nccl_unique_id"); return fail(GGD_EINVAL); }
         ncclUniqueId id;
         memcpy(&id, cfg->nccl_unique_id, sizeof id);
-        ncclResult_t r = ncclCommInitRank(&h->comm, world, id, cfg->rank);
-        if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", ncclGetErrorString(r)); return fail(GGD_ENCCL); }
+        // NCCL shares the SMs with the GEMMs of the backward pass: cap its CTAs so that both fit (tunable)
+        ncclConfig_t ncfg = NCCL_CONFIG_INITIALIZER;
+        const char *mc = getenv("GGD_NCCL_MAX_CTAS");
+        ncfg.maxCTAs = mc ? atoi(mc) : 16;
+        ncfg.minCTAs = ncfg.maxCTAs < 4 ? ncfg.maxCTAs : 4;
+        ncclResult_t r = ncclCommInitRankConfig(&h->comm, world, id, cfg->rank, &ncfg);
+        if (r != ncclSuccess) { set_error("ncclCommInitRankConfig: %s", ncclGetErrorString(r)); return fail(GGD_ENCCL); }
         h->has_comm = true;
+        const char *ov = getenv("GGD_DP_OVERLAP");
+        h->dp_overlap = ov ? atoi(ov) : 1;
     }
 #undef CK
     *out = h;
