@@ -90,7 +90,7 @@ struct ggd_handle {
     // DP
     ncclComm_t comm;
     bool has_comm;
-    int dp_overlap;     // 1: per-layer allreduce + update on the communication stream (default); 0: one allreduce at the end
+    int dp_overlap;     // 0 (default): one allreduce at the end; 1: per-layer allreduce + update on the communication stream
     // host mirrors / stats
     std::vector<float> losses;
     std::vector<float> h_out;
@@ -566,16 +566,18 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         if (!cfg->nccl_unique_id) { set_error("world_size > 1 needs nccl_unique_id"); return fail(GGD_EINVAL); }
         ncclUniqueId id;
         memcpy(&id, cfg->nccl_unique_id, sizeof id);
-        // NCCL shares the SMs with the GEMMs of the backward pass: cap its CTAs so that both fit (tunable)
+        // Measured on 2 x B200 (profiles/r01_dp_sweep_n2.log): one allreduce of the whole gradient arena after the
+        // backward pass (310 us/step) beats per-layer allreduces overlapped with the backward GEMMs (385-580 us/step):
+        // the GEMMs hold every SM with ~190 KB of shared memory, so NCCL's CTAs only run in the gaps.  Both schedules
+        // stay selectable (GGD_DP_OVERLAP, GGD_NCCL_MAX_CTAS) for tuning.
         ncclConfig_t ncfg = NCCL_CONFIG_INITIALIZER;
         const char *mc = getenv("GGD_NCCL_MAX_CTAS");
-        ncfg.maxCTAs = mc ? atoi(mc) : 16;
-        ncfg.minCTAs = ncfg.maxCTAs < 4 ? ncfg.maxCTAs : 4;
+        if (mc) { ncfg.maxCTAs = atoi(mc); ncfg.minCTAs = ncfg.maxCTAs < 4 ? ncfg.maxCTAs : 4; }
         ncclResult_t r = ncclCommInitRankConfig(&h->comm, world, id, cfg->rank, &ncfg);
         if (r != ncclSuccess) { set_error("ncclCommInitRankConfig: %s", ncclGetErrorString(r)); return fail(GGD_ENCCL); }
         h->has_comm = true;
         const char *ov = getenv("GGD_DP_OVERLAP");
-        h->dp_overlap = ov ? atoi(ov) : 1;
+        h->dp_overlap = ov ? atoi(ov) : 0;
     }
 #undef CK
     *out = h;
