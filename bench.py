@@ -104,9 +104,12 @@ def bench_lps(pkg, torch, dev, peaks, with_cpu):
            "roofline": {"bound": "hbm", "achieved": 1540.0 * nf / (kms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                         "frac": 1540.0 * nf / (kms * 1e-3) / 1e9 / peaks["hbm"],
                         "note": "256 int16 in + 257 fp32 out per frame; the kernel is instruction/shared-memory bound (split-radix FFT + double log)"}}
-    h = pcm.cpu().numpy()
+    hp = torch.empty(n, dtype=torch.int16).pin_memory(); hp.copy_(pcm.cpu())
+    ho = torch.empty(nf, 257, dtype=torch.float32).pin_memory()
+    h, feats = hp.numpy(), ho.numpy()
+    ex.extract(h, out=feats)                 # warm: staging buffers of the handle are sized on first use
     t0 = time.perf_counter()
-    feats = ex.extract(h)
+    ex.extract(h, out=feats)                 # pinned host PCM -> device -> kernel -> pinned host features
     dt = time.perf_counter() - t0
     res["e2e"] = {"value": nf / dt, "unit": "frames/s", "h2d_bytes": int(h.nbytes), "d2h_bytes": int(feats.nbytes)}
     if with_cpu:

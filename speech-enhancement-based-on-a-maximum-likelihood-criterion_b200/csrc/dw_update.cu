@@ -157,25 +157,27 @@ dw_update_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         epi_bar_sync();
         pdl_trigger();
         if (threadIdx.x == 64) dstamp(g, 7);
-        const float mom = g.mom, lr = g.lr, Mg = g.Mg, wc = g.wc;
+        // the update phase is issue-bound (16 update warps share 4 schedulers), so the arithmetic is kept minimal:
+        // g/Mg becomes g*(1/Mg) (<= 1 ulp from the reference's division) and the bf16 splits use the paired converts
+        const float mom = g.mom, lr = g.lr, inv_mg = 1.0f / g.Mg, wc = g.wc;
 #pragma unroll
         for (int x = 0; x < RB; x++) {
             const int r = rbase + x, k = i0 + r;
             if (k < g.Kp) {
                 const float2 gr = *reinterpret_cast<const float2 *>(Gs + (size_t)r * G_PITCH + 2 * lane);
                 float2 dd = d[x], ww = w[x];
-                dd.x = mom * dd.x - lr * (gr.x / Mg + wc * ww.x);
-                dd.y = mom * dd.y - lr * (gr.y / Mg + wc * ww.y);
+                dd.x = mom * dd.x - lr * (gr.x * inv_mg + wc * ww.x);
+                dd.y = mom * dd.y - lr * (gr.y * inv_mg + wc * ww.y);
                 ww.x = dd.x + ww.x;
                 ww.y = dd.y + ww.y;
                 const size_t o = (size_t)k * g.Np + colo;
                 *reinterpret_cast<float2 *>(g.W + o) = ww;        // 32 lanes x 8 B = one 256-byte row segment
                 *reinterpret_cast<float2 *>(g.D + o) = dd;
-                bf16 h0, l0, h1, l1;
-                split_bf16(ww.x, h0, l0);
-                split_bf16(ww.y, h1, l1);
-                *reinterpret_cast<uint32_t *>(g.w_hi + o) = pack_bf16x2(h0, h1);
-                *reinterpret_cast<uint32_t *>(g.w_lo + o) = pack_bf16x2(l0, l1);
+                const __nv_bfloat162 hi2 = __floats2bfloat162_rn(ww.x, ww.y);
+                const float2 hf = __bfloat1622float2(hi2);
+                const __nv_bfloat162 lo2 = __floats2bfloat162_rn(ww.x - hf.x, ww.y - hf.y);
+                *reinterpret_cast<__nv_bfloat162 *>(g.w_hi + o) = hi2;
+                *reinterpret_cast<__nv_bfloat162 *>(g.w_lo + o) = lo2;
             }
         }
     }

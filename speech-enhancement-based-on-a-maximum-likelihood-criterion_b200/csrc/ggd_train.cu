@@ -10,6 +10,7 @@
 #include "../../include/ggd_train.h"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "dp_update.cuh"
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -90,6 +91,10 @@ struct ggd_handle {
     // DP
     ncclComm_t comm;
     bool has_comm;
+    bool dp_p2p;        // fused reduce-scatter + sharded update + all-gather over NVLink peer memory (dp_update.cu)
+    DpArgs dpa;
+    void *peer_base[5][DP_MAX_RANKS];   // IPC-mapped peer allocations (G, Phi, Plo, P, flags)
+    unsigned int *dp_flags, *dp_counters;   // local: [2][DP_MAX_RANKS] arrival flags; {step, blocks, error}
     int dp_overlap;     // 0 (default): one allreduce at the end; 1: per-layer allreduce + update on the communication stream
     // host mirrors / stats
     std::vector<float> losses;
@@ -114,6 +119,8 @@ struct ProfScope {
     }
     ~ProfScope() { if (h->prof_on) cudaEventRecord(h->prof_ev.back(), s); }
 };
+
+static int dp_p2p_setup(ggd_handle *h);
 
 static void free_chunk(ggd_handle *h)
 {
@@ -256,6 +263,82 @@ static int ensure_chunk(ggd_handle *h, size_t frames)
     return GGD_OK;
 }
 
+// ---- peer-memory data parallelism: exchange CUDA IPC handles through NCCL, map every peer's arenas -------------
+static int dp_p2p_setup(ggd_handle *h)
+{
+    const int world = h->cfg.world_size, rank = h->cfg.rank;
+    GGD_CUDA(cudaMalloc(&h->dp_flags, 2 * DP_MAX_RANKS * sizeof(unsigned int)));
+    GGD_CUDA(cudaMemset(h->dp_flags, 0, 2 * DP_MAX_RANKS * sizeof(unsigned int)));
+    GGD_CUDA(cudaMalloc(&h->dp_counters, 4 * sizeof(unsigned int)));
+    GGD_CUDA(cudaMemset(h->dp_counters, 0, 4 * sizeof(unsigned int)));
+    void *local[5] = {h->G, h->Phi, h->Plo, h->P, h->dp_flags};
+    cudaIpcMemHandle_t mine[5];
+    for (int k = 0; k < 5; k++) GGD_CUDA(cudaIpcGetMemHandle(&mine[k], local[k]));
+    cudaIpcMemHandle_t *d_all = nullptr, *d_mine = nullptr;
+    GGD_CUDA(cudaMalloc(&d_all, sizeof(mine) * world));
+    GGD_CUDA(cudaMalloc(&d_mine, sizeof(mine)));
+    GGD_CUDA(cudaMemcpy(d_mine, mine, sizeof(mine), cudaMemcpyHostToDevice));
+    GGD_NCCL(ncclAllGather(d_mine, d_all, sizeof(mine), ncclChar, h->comm, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    std::vector<cudaIpcMemHandle_t> all((size_t)5 * world);
+    GGD_CUDA(cudaMemcpy(all.data(), d_all, sizeof(mine) * world, cudaMemcpyDeviceToHost));
+    cudaFree(d_all); cudaFree(d_mine);
+    for (int p = 0; p < world; p++)
+        for (int k = 0; k < 5; k++) {
+            if (p == rank) { h->peer_base[k][p] = local[k]; continue; }
+            cudaError_t e = cudaIpcOpenMemHandle(&h->peer_base[k][p], all[(size_t)p * 5 + k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d, buffer %d): %s", p, k, cudaGetErrorString(e)); return GGD_ECUDA; }
+        }
+    DpArgs &a = h->dpa;
+    memset(&a, 0, sizeof a);
+    for (int p = 0; p < world; p++) {
+        a.G[p] = (float *)h->peer_base[0][p]; a.hi[p] = (bf16 *)h->peer_base[1][p]; a.lo[p] = (bf16 *)h->peer_base[2][p];
+        a.P[p] = (float *)h->peer_base[3][p]; a.flags[p] = (unsigned int *)h->peer_base[4][p];
+    }
+    a.Dl = h->Dl; a.world = world; a.rank = rank;
+    a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
+    a.step_counter = h->dp_counters; a.block_counter = h->dp_counters + 1; a.error_flag = h->dp_counters + 2;
+    a.ctl = h->ctl;
+    // this rank's slice of the arena, cut at float4 granularity, intersected with every weight / bias segment
+    const long long a4 = (long long)h->arena / 4;
+    const long long lo = (a4 * rank / world) * 4, hi = (a4 * (rank + 1) / world) * 4;
+    for (int l = 1; l < h->L; l++) {
+        const LayerInfo &ly = h->lay[l];
+        const long long seg[2][4] = {{(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, 1},
+                                     {(long long)ly.b_off, (long long)ly.gb_off, (long long)ly.Np, 0}};
+        for (int k = 0; k < 2; k++) {
+            const long long s0 = std::max(seg[k][0], lo), s1 = std::min(seg[k][0] + seg[k][2], hi);
+            if (s1 <= s0) continue;
+            if (a.npieces >= 24) { set_error("dp: too many slice pieces"); return GGD_EINVAL; }
+            a.piece[a.npieces++] = {s0, seg[k][1] + (s0 - seg[k][0]), s1 - s0, k == 0 ? h->cfg.weightcost : 0.0f, (int)seg[k][3]};
+        }
+    }
+    h->dp_p2p = true;
+    // nobody may enter the first step before every rank has mapped everyone
+    GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    return GGD_OK;
+}
+
+// after training, the fp32 master of slice p lives on rank p: pull the other slices before exporting weights
+static int dp_p2p_gather_master(ggd_handle *h)
+{
+    const int world = h->cfg.world_size, rank = h->cfg.rank;
+    // every rank must have finished its last step before its slice is read
+    GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    const long long a4 = (long long)h->arena / 4;
+    for (int p = 0; p < world; p++) {
+        if (p == rank) continue;
+        const long long lo = (a4 * p / world) * 4, hi = (a4 * (p + 1) / world) * 4;
+        GGD_CUDA(cudaMemcpy(h->P + lo, (const float *)h->peer_base[3][p] + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault));
+    }
+    // and nobody may resume training (and overwrite its slice) before everyone has copied
+    GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    return GGD_OK;
+}
+
 // ---- one training step (forward, loss gradient, backward, update); stream-ordered, no host sync ----
 static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches)
 {
@@ -313,7 +396,7 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             launch_simt_gemm(h->y32[l - 1], 1, ly.Kp, h->dx32[l], 1, ly.Np, h->G + ly.w_off, ly.Np, ly.prev, ly.cur, h->M, s);
             (*launches)++;
         }
-        if (h->has_comm && apply_update && h->dp_overlap) {
+        if (h->has_comm && apply_update && h->dp_overlap && !h->dp_p2p) {
             // this layer's weight gradient is complete: allreduce it and apply the update on the communication stream
             // while the compute stream continues with the layers below
             GGD_CUDA(cudaEventRecord(h->ev_dw[l], s));
@@ -352,7 +435,10 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
         ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
     };
-    if (h->has_comm && apply_update && !h->dp_overlap) {
+    if (h->has_comm && apply_update && h->dp_p2p) {
+        ProfScope ps(h, KC_UPDATE, s);
+        launch_dp_update(h->dpa, h->sm_count * 4, s); (*launches)++;
+    } else if (h->has_comm && apply_update && !h->dp_overlap) {
         // one allreduce of the whole gradient arena, then the flat update (no overlap; GGD_DP_OVERLAP=0)
         { ProfScope ps(h, KC_ALLREDUCE, s);
           GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena + h->nbias, ncclFloat, ncclSum, h->comm, s)); (*launches)++; }
@@ -474,6 +560,11 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     h->stats.device_ms = ms;
     for (int b = 0; b < nb; b++) h->losses[b] = (float)tr[b];
     h->stats.d2h_bytes = nb * sizeof(double);
+    if (h->dp_p2p) {
+        unsigned int err = 0;
+        GGD_CUDA(cudaMemcpy(&err, h->dp_counters + 2, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) { set_error("data-parallel step: rank %u did not arrive within the timeout (ranks must train the same number of bunches)", err - 1); return GGD_ENCCL; }
+    }
     return GGD_OK;
 }
 
@@ -578,6 +669,11 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         h->has_comm = true;
         const char *ov = getenv("GGD_DP_OVERLAP");
         h->dp_overlap = ov ? atoi(ov) : 0;
+        const char *pm = getenv("GGD_DP_P2P");
+        if (!(pm && atoi(pm) == 0) && world <= DP_MAX_RANKS) {
+            int rc = dp_p2p_setup(h);
+            if (rc != GGD_OK) return fail(rc);
+        }
     }
 #undef CK
     *out = h;
@@ -591,6 +687,10 @@ int ggd_destroy(ggd_handle *h)
     if (h->s_main) cudaStreamSynchronize(h->s_main);
     free_chunk(h);
     for (auto &kv : h->pinned) if (kv.second) cudaHostUnregister(const_cast<void *>(kv.first));
+    if (h->dp_p2p)
+        for (int p = 0; p < h->cfg.world_size; p++)
+            for (int k = 0; k < 5; k++) if (p != h->cfg.rank && h->peer_base[k][p]) cudaIpcCloseMemHandle(h->peer_base[k][p]);
+    cudaFree(h->dp_flags); cudaFree(h->dp_counters);
     if (h->has_comm) ncclCommDestroy(h->comm);
     cudaFree(h->P); cudaFree(h->Dl); cudaFree(h->G); cudaFree(h->Phi); cudaFree(h->Plo);
     for (int l = 0; l < GGD_MAXLAYER; l++) {
@@ -760,6 +860,7 @@ int ggd_get_weights(ggd_handle *h, float *const *weights, float *const *bias)
     if (!h || !weights || !bias) { set_error("ggd_get_weights: bad argument"); return GGD_EINVAL; }
     GGD_CUDA(cudaSetDevice(h->cfg.gpu));
     GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    if (h->dp_p2p) GGD_TRY(dp_p2p_gather_master(h));
     for (int l = 1; l < h->L; l++) {
         const LayerInfo &ly = h->lay[l];
         GGD_CUDA(cudaMemcpy2D(weights[l], ly.cur * sizeof(float), h->P + ly.w_off, ly.Np * sizeof(float), ly.cur * sizeof(float), ly.prev, cudaMemcpyDeviceToHost));

@@ -63,10 +63,12 @@ class Wav2LPS:
         assert mean.size == 257 and dvar.size == 257
         self._ck(self.L.lps_set_norm(self.h, mean.ctypes.data_as(PF), dvar.ctypes.data_as(PF)))
 
-    def extract(self, pcm, flags=0):
+    def extract(self, pcm, flags=0, out=None):
         pcm = np.ascontiguousarray(pcm, np.int16)
         nf = lps_nframes(pcm.size)
-        out = np.zeros((nf, 257), np.float32)
+        if out is None:
+            out = np.zeros((nf, 257), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size >= nf * 257
         self._ck(self.L.lps_extract(self.h, pcm.ctypes.data_as(PS), pcm.size, out.ctypes.data_as(PF), flags))
         return out
 
