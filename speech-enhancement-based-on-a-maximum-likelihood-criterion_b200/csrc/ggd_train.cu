@@ -92,9 +92,9 @@ struct ggd_handle {
     ncclComm_t comm;
     bool has_comm;
     bool dp_p2p;        // fused reduce-scatter + sharded update + all-gather over NVLink peer memory (dp_update.cu)
-    DpArgs dpa;
+    DpArgs dpa[GGD_MAXLAYER];   // one fused exchange+update launch per layer (index = layer; biases ride with layer 1)
     void *peer_base[5][DP_MAX_RANKS];   // IPC-mapped peer allocations (G, Phi, Plo, P, flags)
-    unsigned int *dp_flags, *dp_counters;   // local: [2][DP_MAX_RANKS] arrival flags; {step, blocks, error}
+    unsigned int *dp_flags, *dp_counters;   // local: per layer [2][DP_MAX_RANKS] arrival flags; per layer {step, blocks}, then {error}
     int dp_overlap;     // 0 (default): one allreduce at the end; 1: per-layer allreduce + update on the communication stream
     // host mirrors / stats
     std::vector<float> losses;
@@ -267,10 +267,11 @@ static int ensure_chunk(ggd_handle *h, size_t frames)
 static int dp_p2p_setup(ggd_handle *h)
 {
     const int world = h->cfg.world_size, rank = h->cfg.rank;
-    GGD_CUDA(cudaMalloc(&h->dp_flags, 2 * DP_MAX_RANKS * sizeof(unsigned int)));
-    GGD_CUDA(cudaMemset(h->dp_flags, 0, 2 * DP_MAX_RANKS * sizeof(unsigned int)));
-    GGD_CUDA(cudaMalloc(&h->dp_counters, 4 * sizeof(unsigned int)));
-    GGD_CUDA(cudaMemset(h->dp_counters, 0, 4 * sizeof(unsigned int)));
+    const size_t nflags = (size_t)GGD_MAXLAYER * 2 * DP_MAX_RANKS, ncnt = (size_t)GGD_MAXLAYER * 2 + 2;
+    GGD_CUDA(cudaMalloc(&h->dp_flags, nflags * sizeof(unsigned int)));
+    GGD_CUDA(cudaMemset(h->dp_flags, 0, nflags * sizeof(unsigned int)));
+    GGD_CUDA(cudaMalloc(&h->dp_counters, ncnt * sizeof(unsigned int)));
+    GGD_CUDA(cudaMemset(h->dp_counters, 0, ncnt * sizeof(unsigned int)));
     void *local[5] = {h->G, h->Phi, h->Plo, h->P, h->dp_flags};
     cudaIpcMemHandle_t mine[5];
     for (int k = 0; k < 5; k++) GGD_CUDA(cudaIpcGetMemHandle(&mine[k], local[k]));
@@ -289,28 +290,30 @@ static int dp_p2p_setup(ggd_handle *h)
             cudaError_t e = cudaIpcOpenMemHandle(&h->peer_base[k][p], all[(size_t)p * 5 + k], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d, buffer %d): %s", p, k, cudaGetErrorString(e)); return GGD_ECUDA; }
         }
-    DpArgs &a = h->dpa;
-    memset(&a, 0, sizeof a);
-    for (int p = 0; p < world; p++) {
-        a.G[p] = (float *)h->peer_base[0][p]; a.hi[p] = (bf16 *)h->peer_base[1][p]; a.lo[p] = (bf16 *)h->peer_base[2][p];
-        a.P[p] = (float *)h->peer_base[3][p]; a.flags[p] = (unsigned int *)h->peer_base[4][p];
-    }
-    a.Dl = h->Dl; a.world = world; a.rank = rank;
-    a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
-    a.step_counter = h->dp_counters; a.block_counter = h->dp_counters + 1; a.error_flag = h->dp_counters + 2;
-    a.ctl = h->ctl;
-    // this rank's slice of the arena, cut at float4 granularity, intersected with every weight / bias segment
-    const long long a4 = (long long)h->arena / 4;
-    const long long lo = (a4 * rank / world) * 4, hi = (a4 * (rank + 1) / world) * 4;
+    // Ownership: rank r owns the r-th 1/world of EVERY weight matrix and of every bias vector (float4 granularity), so
+    // that each per-layer launch is balanced.  Layer l's launch handles W_l; layer 1's launch (the last of a step) also
+    // handles all biases, whose gradients only exist after the bias-gradient kernel.
+    auto add_piece = [&](DpArgs &a, long long off, long long goff, long long n, float wc, int shadow) {
+        const long long n4 = n / 4, lo = (n4 * rank / world) * 4, hi = (n4 * (rank + 1) / world) * 4;
+        if (hi > lo && a.npieces < 24) a.piece[a.npieces++] = {off + lo, goff + lo, hi - lo, wc, shadow};
+    };
     for (int l = 1; l < h->L; l++) {
+        DpArgs &a = h->dpa[l];
+        memset(&a, 0, sizeof a);
+        for (int p = 0; p < world; p++) {
+            a.G[p] = (float *)h->peer_base[0][p]; a.hi[p] = (bf16 *)h->peer_base[1][p]; a.lo[p] = (bf16 *)h->peer_base[2][p];
+            a.P[p] = (float *)h->peer_base[3][p];
+            a.flags[p] = (unsigned int *)h->peer_base[4][p] + (size_t)l * 2 * DP_MAX_RANKS;
+        }
+        a.Dl = h->Dl; a.world = world; a.rank = rank;
+        a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
+        a.step_counter = h->dp_counters + 2 * l; a.block_counter = h->dp_counters + 2 * l + 1;
+        a.error_flag = h->dp_counters + 2 * GGD_MAXLAYER;
         const LayerInfo &ly = h->lay[l];
-        const long long seg[2][4] = {{(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, 1},
-                                     {(long long)ly.b_off, (long long)ly.gb_off, (long long)ly.Np, 0}};
-        for (int k = 0; k < 2; k++) {
-            const long long s0 = std::max(seg[k][0], lo), s1 = std::min(seg[k][0] + seg[k][2], hi);
-            if (s1 <= s0) continue;
-            if (a.npieces >= 24) { set_error("dp: too many slice pieces"); return GGD_EINVAL; }
-            a.piece[a.npieces++] = {s0, seg[k][1] + (s0 - seg[k][0]), s1 - s0, k == 0 ? h->cfg.weightcost : 0.0f, (int)seg[k][3]};
+        add_piece(a, (long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1);
+        if (l == 1) {
+            for (int k = 1; k < h->L; k++) add_piece(a, (long long)h->lay[k].b_off, (long long)h->lay[k].gb_off, (long long)h->lay[k].Np, 0.0f, 0);
+            a.ctl = h->ctl;    // last launch of a step: advances the bunch counter
         }
     }
     h->dp_p2p = true;
@@ -327,11 +330,14 @@ static int dp_p2p_gather_master(ggd_handle *h)
     // every rank must have finished its last step before its slice is read
     GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
     GGD_CUDA(cudaStreamSynchronize(h->s_main));
-    const long long a4 = (long long)h->arena / 4;
     for (int p = 0; p < world; p++) {
         if (p == rank) continue;
-        const long long lo = (a4 * p / world) * 4, hi = (a4 * (p + 1) / world) * 4;
-        GGD_CUDA(cudaMemcpy(h->P + lo, (const float *)h->peer_base[3][p] + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault));
+        for (int l = 1; l < h->L; l++) {
+            const LayerInfo &ly = h->lay[l];
+            const long long n4 = (long long)ly.Kp * ly.Np / 4, lo = (n4 * p / world) * 4, hi = (n4 * (p + 1) / world) * 4;
+            if (hi > lo)
+                GGD_CUDA(cudaMemcpy(h->P + ly.w_off + lo, (const float *)h->peer_base[3][p] + ly.w_off + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault));
+        }
     }
     // and nobody may resume training (and overwrite its slice) before everyone has copied
     GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
@@ -396,6 +402,14 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             launch_simt_gemm(h->y32[l - 1], 1, ly.Kp, h->dx32[l], 1, ly.Np, h->G + ly.w_off, ly.Np, ly.prev, ly.cur, h->M, s);
             (*launches)++;
         }
+        if (h->has_comm && apply_update && h->dp_p2p && l != 1) {
+            // fused NVLink exchange + sharded update of this layer on the communication stream (its blocks use no shared
+            // memory, so they co-reside with the GEMM CTAs of the layers below)
+            GGD_CUDA(cudaEventRecord(h->ev_dw[l], s));
+            GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_dw[l], 0));
+            ProfScope ps(h, KC_UPDATE, h->s_comm);
+            launch_dp_update(h->dpa[l], h->sm_count * 2, h->s_comm); (*launches)++;
+        }
         if (h->has_comm && apply_update && h->dp_overlap && !h->dp_p2p) {
             // this layer's weight gradient is complete: allreduce it and apply the update on the communication stream
             // while the compute stream continues with the layers below
@@ -436,8 +450,13 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
     };
     if (h->has_comm && apply_update && h->dp_p2p) {
-        ProfScope ps(h, KC_UPDATE, s);
-        launch_dp_update(h->dpa, h->sm_count * 4, s); (*launches)++;
+        // layers L-1..2 were exchanged and updated on the communication stream while the backward pass went on (see the
+        // loop above); layer 1 and the biases follow now, then the streams join
+        GGD_CUDA(cudaEventRecord(h->ev_bias, s));
+        GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_bias, 0));
+        { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_dp_update(h->dpa[1], h->sm_count * 2, h->s_comm); (*launches)++; }
+        GGD_CUDA(cudaEventRecord(h->ev_done, h->s_comm));
+        GGD_CUDA(cudaStreamWaitEvent(s, h->ev_done, 0));
     } else if (h->has_comm && apply_update && !h->dp_overlap) {
         // one allreduce of the whole gradient arena, then the flat update (no overlap; GGD_DP_OVERLAP=0)
         { ProfScope ps(h, KC_ALLREDUCE, s);
@@ -562,7 +581,7 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     h->stats.d2h_bytes = nb * sizeof(double);
     if (h->dp_p2p) {
         unsigned int err = 0;
-        GGD_CUDA(cudaMemcpy(&err, h->dp_counters + 2, sizeof err, cudaMemcpyDeviceToHost));
+        GGD_CUDA(cudaMemcpy(&err, h->dp_counters + 2 * GGD_MAXLAYER, sizeof err, cudaMemcpyDeviceToHost));
         if (err) { set_error("data-parallel step: rank %u did not arrive within the timeout (ranks must train the same number of bunches)", err - 1); return GGD_ENCCL; }
     }
     return GGD_OK;
@@ -670,7 +689,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         const char *ov = getenv("GGD_DP_OVERLAP");
         h->dp_overlap = ov ? atoi(ov) : 0;
         const char *pm = getenv("GGD_DP_P2P");
-        if (!(pm && atoi(pm) == 0) && world <= DP_MAX_RANKS) {
+        if (!(pm && atoi(pm) == 0) && world <= DP_MAX_RANKS && h->tensor) {   // (the fp32 validation path reads the master weights)
             int rc = dp_p2p_setup(h);
             if (rc != GGD_OK) return fail(rc);
         }
