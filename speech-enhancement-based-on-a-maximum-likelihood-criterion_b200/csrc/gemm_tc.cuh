@@ -81,6 +81,34 @@ struct DwUpdPlan {
 };
 int launch_dw_update(const DwUpdPlan &p, cudaStream_t s);
 int dw_update_init();
+
+// ---- persistent gradient + update kernel for ALL layers and biases in one launch (dw_persist.cu; Mp == 128) ---------
+// The argument block lives in device memory (its tensor maps are read by TMA from there).
+struct DwpLayer {
+    CUtensorMap a_hi, a_lo;   // dE/dx of this layer, bf16 [Mp][Np], box {64 units, 64 frames}
+    CUtensorMap b_hi, b_lo;   // activations of the layer below (chunk input for layer 1), bf16 [rows][Kp], box {64, 64}
+    float *W, *D;             // fp32 weights / momentum [Kp][Np]
+    bf16 *w_hi, *w_lo;        // shadows [Kp][Np]
+    float *b, *db;            // bias and its momentum
+    const bf16 *dx_hi, *dx_lo;  // same arrays as a_hi / a_lo, for the bias gradient
+    int Kp, Np, N;            // padded dims, real output units
+    int k_tiles;              // Kp / 64
+    int tile_base;            // index of this layer's first tile in the global list
+    int b_rows_from_ctl;      // add ctl->bunch_idx * rows_per_bunch to the frame coordinate of b_hi / b_lo
+    float wc;
+    int pad;
+};
+struct DwpArgs {
+    DwpLayer layer[10];
+    int nlayers, total_tiles;
+    StepCtl *ctl;
+    int rows_per_bunch, M;
+    float mom, lr, Mg;
+    int advance;                  // last CTA out increments ctl->bunch_idx
+    unsigned int *done_counter;
+};
+int launch_dw_persist(const DwpArgs *dev_args, int grid, cudaStream_t s);
+int dw_persist_init();
 int gemm_tc_init();   // resolves the driver entry point, sets the shared-memory attributes
 
 }  // namespace ggd

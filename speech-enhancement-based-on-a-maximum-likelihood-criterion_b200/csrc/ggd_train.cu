@@ -85,6 +85,9 @@ struct ggd_handle {
     GemmPlan fwd[GGD_MAXLAYER], dxp[GGD_MAXLAYER], dwp[GGD_MAXLAYER];
     DwUpdPlan dwu[GGD_MAXLAYER];
     bool fused;         // gradient GEMM + update fused (single GPU, tensor path)
+    bool persist;       // fused AND the bunch is one reduction tile: one persistent launch for all layers (dw_persist.cu)
+    DwpArgs *dwp_dev;   // its argument block (device memory)
+    unsigned int *dwp_counter;
     cudaGraphExec_t g1, gN;
     int gN_steps;
     int launches_per_step;
@@ -235,6 +238,32 @@ static int build_plans(ggd_handle *h)
             a.w_hi = h->Phi + ly.w_off; a.w_lo = h->Plo + ly.w_off;
             a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg; a.wc = h->cfg.weightcost;
         }
+    }
+    if (h->persist) {
+        // one tile list over all layers: (layer, 128-unit n-tile, 64-unit k-tile), k fastest
+        DwpArgs a;
+        memset(&a, 0, sizeof a);
+        int base = 0;
+        for (int l = 1; l < L; l++) {
+            const LayerInfo &ly = h->lay[l];
+            DwpLayer &d = a.layer[a.nlayers++];
+            d.a_hi = h->dwu[l].b_hi; d.a_lo = h->dwu[l].b_lo;   // dE/dx, box {64, 64}
+            d.b_hi = h->dwu[l].a_hi; d.b_lo = h->dwu[l].a_lo;   // activations below, box {64, 64}
+            d.W = h->P + ly.w_off; d.D = h->Dl + ly.w_off; d.w_hi = h->Phi + ly.w_off; d.w_lo = h->Plo + ly.w_off;
+            d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off;
+            d.dx_hi = h->dx_hi[l]; d.dx_lo = h->dx_lo[l];
+            d.Kp = ly.Kp; d.Np = ly.Np; d.N = ly.cur;
+            d.k_tiles = ly.Kp / 64;
+            d.tile_base = base;
+            d.b_rows_from_ctl = (l == 1);
+            d.wc = h->cfg.weightcost;
+            base += ceil_div(ly.Np, 128) * d.k_tiles;
+        }
+        a.total_tiles = base;
+        a.ctl = h->ctl; a.rows_per_bunch = h->M; a.M = h->M;
+        a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
+        a.advance = 1; a.done_counter = h->dwp_counter;
+        GGD_CUDA(cudaMemcpy(h->dwp_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     }
     return GGD_OK;
 }
@@ -391,7 +420,8 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         const LayerInfo &ly = h->lay[l];
         if (h->tensor) {
             if (l != 1) { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
-            if (fused) { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_update(h->dwu[l], s)); (*launches)++; }
+            if (fused && h->persist) { /* all layers in one persistent launch after the backward chain */ }
+            else if (fused) { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_update(h->dwu[l], s)); (*launches)++; }
             else { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
         } else {
             if (l != L - 1) { launch_simt_dsigmoid(h->y32[l], h->dy32[l], h->dx32[l], ly.Np, h->M, ly.cur, s); (*launches)++; }
@@ -424,6 +454,13 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
             { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_update(ua, h->sm_count / 2, h->s_comm); (*launches)++; }
         }
+    }
+    if (fused && h->persist) {
+        // weight gradients + updates of all layers, bias gradients + updates and the bunch counter: one launch
+        ProfScope ps(h, KC_DWUPD, s);
+        GGD_TRY(launch_dw_persist(h->dwp_dev, h->sm_count, s)); (*launches)++;
+        GGD_CUDA(cudaGetLastError());
+        return GGD_OK;
     }
     {
         ProfScope ps(h, KC_BIAS, s);
@@ -616,6 +653,10 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     h->sm_count = prop.multiProcessorCount;
     h->tensor = (cfg->precision == GGD_PREC_BF16X3);
     h->fused = h->tensor && !(cfg->world_size > 1) && !(cfg->flags & GGD_FLAG_UNFUSED_UPDATE);
+    {
+        const char *ev = getenv("GGD_DW_PERSIST");   // 0: per-layer dw_update launches (tuning / A-B only)
+        h->persist = h->fused && h->Mp == 128 && !(ev && atoi(ev) == 0);
+    }
     const int world = cfg->world_size > 1 ? cfg->world_size : 1;
     h->Mg = h->M * world;
     size_t off = 0;
@@ -662,6 +703,8 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     CK(cudaMalloc(&h->alpha, D * sizeof(float))); CK(cudaMalloc(&h->colsum, D * sizeof(float)));
     CK(cudaMemset(h->alpha, 0, D * sizeof(float))); CK(cudaMemset(h->colsum, 0, D * sizeof(float)));
     CK(cudaMalloc(&h->ctl, sizeof(StepCtl))); CK(cudaMemset(h->ctl, 0, sizeof(StepCtl)));
+    CK(cudaMalloc(&h->dwp_dev, sizeof(DwpArgs))); CK(cudaMalloc(&h->dwp_counter, sizeof(unsigned int)));
+    CK(cudaMemset(h->dwp_counter, 0, sizeof(unsigned int)));
     // weights in: reference order (out + in*cur) -> padded pitch Np; then build the bf16 shadows with a zero-gradient-free pass
     for (int l = 1; l < h->L; l++) {
         const LayerInfo &ly = h->lay[l];
@@ -671,7 +714,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         launch_split_rows(h->P + ly.w_off, ly.Kp, ly.Np, h->Phi + ly.w_off, h->Plo + ly.w_off, ly.Np, 0);
     }
     CK(cudaDeviceSynchronize());
-    if (h->tensor) { int rc = gemm_tc_init(); if (rc == GGD_OK) rc = dw_update_init(); if (rc != GGD_OK) return fail(rc); }
+    if (h->tensor) { int rc = gemm_tc_init(); if (rc == GGD_OK) rc = dw_update_init(); if (rc == GGD_OK) rc = dw_persist_init(); if (rc != GGD_OK) return fail(rc); }
     if (world > 1) {
         if (!cfg->nccl_unique_id) { set_error("world_size > 1 needs nccl_unique_id"); return fail(GGD_EINVAL); }
         ncclUniqueId id;
@@ -716,7 +759,7 @@ int ggd_destroy(ggd_handle *h)
         cudaFree(h->act_hi[l]); cudaFree(h->act_lo[l]); cudaFree(h->dx_hi[l]); cudaFree(h->dx_lo[l]);
         cudaFree(h->x32[l]); cudaFree(h->y32[l]); cudaFree(h->dy32[l]); cudaFree(h->dx32[l]);
     }
-    cudaFree(h->out32); cudaFree(h->alpha); cudaFree(h->colsum); cudaFree(h->ctl);
+    cudaFree(h->out32); cudaFree(h->alpha); cudaFree(h->colsum); cudaFree(h->ctl); cudaFree(h->dwp_dev); cudaFree(h->dwp_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);

@@ -140,3 +140,27 @@ def test_fused_update_equals_unfused(pkg, oracle):
     orc.train(x, t)
     for u, v in zip(Wa + ba, orc.weights()[0] + orc.weights()[1]):
         assert rel_err(u, v) < 1e-3
+
+
+def test_named_shape_chunk_persistent(pkg, oracle):
+    """ggd_train at the named shape: the production path (graph replay, persistent gradient+update launch for all
+    layers, biases and the bunch counter) over several bunches against the C oracle"""
+    O = oracle
+    layersizes, M, nb = [1799, 2048, 2048, 2048, 257], 128, 5
+    W, b, x, t = make_case(O, layersizes, M * nb, 21)
+    orc = O.OracleNet(layersizes, M, 0.1, 0.9, 1e-5, 1.5, 1, W, b)
+    lo, al = orc.train(x, t)
+    net = pkg.BP_GPU(0, 0, 5, layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1)
+    net.train(x.shape[0], x, t)
+    lg = net.losses()
+    assert len(lg) == nb
+    assert np.max(np.abs(lg - lo) / np.abs(lo)) < 5e-3
+    assert rel_err(net.alpha(), al[-1]) < 1e-3
+    Wg, bg = net.returnWeights()
+    Wo, bo = orc.weights()
+    for l in range(4):
+        assert rel_err(Wg[l], Wo[l]) < 1e-3
+        assert rel_err(bg[l], bo[l]) < 1e-3
+        # the UPDATE itself must agree, not only the (barely moved) weights
+        assert rel_err(Wg[l] - W[l], Wo[l] - W[l]) < 2e-3, l
+        assert rel_err(bg[l] - b[l], bo[l] - b[l]) < 2e-3, l
