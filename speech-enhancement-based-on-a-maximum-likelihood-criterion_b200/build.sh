@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds libggd_b200.so (trainer + LPS kernels, C ABI in include/*.h) for sm_100a, in-tree.
-set -e
+set -e -o pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 -ccbin /usr/bin/g++"

@@ -11,11 +11,13 @@
 // coalesced straight from registers, with no shared-memory transposition and no staging buffer.
 //
 // CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = update warps.
-//   * dx^T tile of the current n-tile (128 n x 128 frames, bf16 hi/lo, 64 KB) stays RESIDENT in one of two slots while
-//     the CTA walks the k-tiles; only the y^T tile (64 k x 128 frames, 32 KB) streams through a 3-stage ring.
+//   * dx^T tile of the current n-tile (128 n x 128 frames, bf16 hi/lo, 64 KB) stays RESIDENT while the CTA walks the
+//     k-tiles; only the y^T tile (64 k x 128 frames, 32 KB) streams through a 2-stage ring.
 //   * the accumulator is double-buffered in TMEM (2 x 64 columns): the MMAs of tile t+1 run under the update of tile t.
-//   * every update thread keeps the W / delta values of the NEXT tile in flight (64 independent loads) while it stores
-//     the current one, so the kernel is a continuous HBM stream: 16 B/param (+4 B/param of bf16 shadows).
+//   * the fp32 weights and momentum stream in by TMA as well (half tiles: 32 k x 128 n of W and of delta, 32 KB per
+//     stage, 3 stages = 1.5 tiles ahead of the update warps), so ~96 KB of HBM reads per SM are always in flight
+//     without holding a single register; the update warps read them conflict-free from shared memory (lane = n) and
+//     store W, delta and the bf16 shadows straight from registers: 16 B/param (+4 B/param of bf16 shadows).
 // The CTA that owns k-tile 0 of an n-tile also forms the bias gradient of those 128 units (column sums of dx over the
 // frames) and applies the bias update; the last CTA to finish advances the device-side bunch counter.
 #include "gemm_tc.cuh"
@@ -31,8 +33,12 @@ constexpr int A_PART = 2 * A_HALF;                 // 16 KB: 128 n x 64 frames (
 constexpr int A_SLOT = KB * 2 * A_PART;            // 64 KB
 constexpr int B_PART = TK * BK * 2;                // 8 KB
 constexpr int B_STAGE = KB * 2 * B_PART;           // 32 KB
-constexpr int A_SLOTS = 2, B_STAGES = 3;
-constexpr int SMEM = A_SLOTS * A_SLOT + B_STAGES * B_STAGE + 1024;
+constexpr int A_SLOTS = 1, B_STAGES = 2;
+constexpr int WD_ROWS = 32;                        // k rows per W/delta half-tile stage
+constexpr int WD_PART = WD_ROWS * TN * 4;          // 16 KB: 32 k x 128 n fp32
+constexpr int WD_STAGE = 2 * WD_PART;              // W then delta
+constexpr int WD_STAGES = 3;
+constexpr int SMEM = A_SLOTS * A_SLOT + B_STAGES * B_STAGE + WD_STAGES * WD_STAGE + 1024;
 constexpr int NTHREADS = 320;
 constexpr int TMEM_COLS = 2 * TK;                  // double-buffered accumulator
 }  // namespace dwp
@@ -56,28 +62,35 @@ __device__ __forceinline__ TileRef decode_tile(const DwpArgs *gp, int t)
     return tr;
 }
 
-__device__ __forceinline__ float ld_stream_f32(const float *p)
+// Bounded mbarrier wait: a pipeline bug must surface as an error, never as a hung GPU.  After ~2^22 failed probes
+// (seconds) the waiter records {code, block, iteration, parity} in host-mapped memory and traps.
+__device__ __noinline__ void hang_report(unsigned int *rec, int code, int it, uint32_t parity)
 {
-    float v;
-    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
+    if (rec) {
+        rec[1] = (unsigned int)code; rec[2] = blockIdx.x; rec[3] = (unsigned int)it; rec[4] = parity; rec[5] = threadIdx.x;
+        __threadfence_system();
+        rec[0] = 0xDEADu;
+        __threadfence_system();
+    }
+    __trap();
 }
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, unsigned int *rec, int code, int it)
+{
+    unsigned int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        ++spins;
+        if (spins == (1u << 16) && rec && (threadIdx.x & 31) == 0) {   // note who is waiting on what, per warp
+            unsigned int *w = rec + 8 + (blockIdx.x * 10 + (threadIdx.x >> 5)) * 4;
+            w[0] = (unsigned int)code; w[1] = (unsigned int)it; w[2] = parity; w[3] |= 0x80000000u;
+            __threadfence_system();
+        }
+        if (spins > (1u << 22)) hang_report(rec, code, it, parity);
+    }
+}
+
 __device__ __forceinline__ void st_stream_f32(float *p, float v)
 {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-
-__device__ __forceinline__ void load_wd16(const float *W, const float *D, size_t off, int Np, bool ok, float *w, float *d)
-{
-#pragma unroll
-    for (int x = 0; x < 16; x++) {
-        if (ok) {
-            w[x] = ld_stream_f32(W + off + (size_t)x * Np);
-            d[x] = ld_stream_f32(D + off + (size_t)x * Np);
-        } else {
-            w[x] = 0.0f; d[x] = 0.0f;
-        }
-    }
 }
 
 __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpArgs *__restrict__ gp)
@@ -85,8 +98,9 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
     using namespace dwp;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *a_slots = smem, *b_ring = smem + A_SLOTS * A_SLOT;
+    uint8_t *a_slots = smem, *b_ring = smem + A_SLOTS * A_SLOT, *wd_ring = b_ring + B_STAGES * B_STAGE;
     __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS], b_full[B_STAGES], b_empty[B_STAGES], t_full[2], t_empty[2];
+    __shared__ __align__(8) uint64_t wd_full[WD_STAGES], wd_empty[WD_STAGES];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,6 +112,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
             for (int s = 0; s < A_SLOTS; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
             for (int s = 0; s < B_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
             for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
+            for (int s = 0; s < WD_STAGES; s++) { mbar_init(&wd_full[s], 1); mbar_init(&wd_empty[s], 8); }
             fence_mbar_init();
         }
         __syncwarp();
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                     key = tr.key;
                     const int sl = a_cnt % A_SLOTS, ph = (a_cnt / A_SLOTS) & 1;
                     a_cnt++;
-                    mbar_wait(&a_empty[sl], ph ^ 1);
+                    mbar_wait_bounded(&a_empty[sl], ph ^ 1, gp->hang, 1, it);
                     mbar_expect_tx(&a_full[sl], A_SLOT);
                     uint8_t *dst = a_slots + sl * A_SLOT;
 #pragma unroll
@@ -133,7 +148,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                         }
                 }
                 const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
-                mbar_wait(&b_empty[s], ph ^ 1);
+                mbar_wait_bounded(&b_empty[s], ph ^ 1, gp->hang, 2, it);
                 mbar_expect_tx(&b_full[s], B_STAGE);
                 uint8_t *dst = b_ring + s * B_STAGE;
                 const int r0 = L->b_rows_from_ctl ? bunch_row0 : 0;
@@ -141,6 +156,16 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                 for (int kb = 0; kb < KB; kb++) {
                     tma_load_2d(dst + kb * 2 * B_PART, &L->b_hi, &b_full[s], tr.kt * TK, r0 + kb * BK);
                     tma_load_2d(dst + kb * 2 * B_PART + B_PART, &L->b_lo, &b_full[s], tr.kt * TK, r0 + kb * BK);
+                }
+                // fp32 weights / momentum of this tile: two half tiles of 32 k rows
+#pragma unroll
+                for (int hs = 0; hs < 2; hs++) {
+                    const int seq = 2 * it + hs, ws = seq % WD_STAGES, wph = (seq / WD_STAGES) & 1;
+                    mbar_wait_bounded(&wd_empty[ws], wph ^ 1, gp->hang, 3, it);
+                    mbar_expect_tx(&wd_full[ws], WD_STAGE);
+                    uint8_t *wdst = wd_ring + ws * WD_STAGE;
+                    tma_load_2d(wdst, &L->w_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + hs * WD_ROWS);
+                    tma_load_2d(wdst + WD_PART, &L->d_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + hs * WD_ROWS);
                 }
             }
         }
@@ -155,13 +180,13 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                 if (tr.key != key) {
                     key = tr.key;
                     sl = a_cnt % A_SLOTS;
-                    mbar_wait(&a_full[sl], (a_cnt / A_SLOTS) & 1);
+                    mbar_wait_bounded(&a_full[sl], (a_cnt / A_SLOTS) & 1, gp->hang, 4, it);
                     a_cnt++;
                 }
                 const int s = it % B_STAGES;
-                mbar_wait(&b_full[s], (it / B_STAGES) & 1);
+                mbar_wait_bounded(&b_full[s], (it / B_STAGES) & 1, gp->hang, 5, it);
                 const int acc = it & 1;
-                mbar_wait(&t_empty[acc], ((it >> 1) & 1) ^ 1);
+                mbar_wait_bounded(&t_empty[acc], ((it >> 1) & 1) ^ 1, gp->hang, 6, it);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(a_slots + sl * A_SLOT), b0 = smem_u32(b_ring + s * B_STAGE);
                 const uint32_t d = tmem + acc * TK;
@@ -191,15 +216,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
         // ===== update warps (8): quadrant q = lanes [32q, 32q+32) of the accumulator, `half` = 32 of its 64 columns =====
         const int e = warp - 2, q = warp & 3, half = e >> 2;
         const float mom = gp->mom, lr = gp->lr, inv_mg = 1.0f / gp->Mg;
-        float w[32], d[32];
         TileRef tr = decode_tile(gp, t0);
-        {
-            const DwpLayer *L = tr.L;
-            const int n = tr.nt * TN + q * 32 + lane;
-            const size_t off = (size_t)(tr.kt * TK + half * 32) * L->Np + n;
-            load_wd16(L->W, L->D, off, L->Np, n < L->Np, w, d);
-            load_wd16(L->W, L->D, off + (size_t)16 * L->Np, L->Np, n < L->Np, w + 16, d + 16);
-        }
         for (int t = t0, it = 0; t < t1; t++, it++) {
             const DwpLayer *L = tr.L;
             float *W = L->W, *D = L->D;
@@ -209,32 +226,48 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
             const int n = tr.nt * TN + q * 32 + lane;
             const bool ok = n < Np;
             const size_t off0 = (size_t)(tr.kt * TK + half * 32) * Np + n;
-            const bool has_next = t + 1 < t1;
             TileRef nx = tr;
-            if (has_next) nx = decode_tile(gp, t + 1);
-            const DwpLayer *Ln = nx.L;
-            const int nn = nx.nt * TN + q * 32 + lane;
-            const size_t noff0 = (size_t)(nx.kt * TK + half * 32) * Ln->Np + nn;
+            if (t + 1 < t1) nx = decode_tile(gp, t + 1);
 
+            if (gp->dbg_progress && lane == 0) { gp->hang[8 + (blockIdx.x * 10 + warp) * 4 + 3] = 1000u + (unsigned int)it; }
             const int acc = it & 1;
-            mbar_wait(&t_full[acc], (it >> 1) & 1);
+            // Every update warp follows EVERY stage of the W/delta ring in order (full -> empty), although it only reads
+            // the half tile of its own `half`: a warp that skipped the other half's stages could get two phases away from
+            // a barrier (TMA loads land out of order) and a parity wait cannot tell phase f from phase f+2.
+            const int seq = 2 * it + half, ws = seq % WD_STAGES;
+            const int oseq = 2 * it + (half ^ 1), ows = oseq % WD_STAGES;
+            const float *ws_w = reinterpret_cast<const float *>(wd_ring + ws * WD_STAGE) + q * 32 + lane;
+            const float *ws_d = ws_w + WD_PART / 4;
+            if (half == 0) {
+                mbar_wait_bounded(&wd_full[ws], (seq / WD_STAGES) & 1, gp->hang, 7, it);
+                mbar_wait_bounded(&wd_full[ows], (oseq / WD_STAGES) & 1, gp->hang, 9, it);
+            } else {
+                mbar_wait_bounded(&wd_full[ows], (oseq / WD_STAGES) & 1, gp->hang, 9, it);
+                mbar_wait_bounded(&wd_full[ws], (seq / WD_STAGES) & 1, gp->hang, 7, it);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&wd_empty[ows]);   // not read by this warp
+            mbar_wait_bounded(&t_full[acc], (it >> 1) & 1, gp->hang, 8, it);
+            __syncwarp();
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * TK + half * 32;
 #pragma unroll
             for (int c = 0; c < 32; c += 16) {
-                float g[16];
+                float g[16], w[16], d[16];
+#pragma unroll
+                for (int x = 0; x < 16; x++) { w[x] = ws_w[(c + x) * TN]; d[x] = ws_d[(c + x) * TN]; }
                 tmem_ld16(taddr + c, g);
-                if (c == 16) {   // the accumulator has been drained by this warp: hand it back to the MMA issuer
+                if (c == 16) {   // accumulator and W/delta stage have been drained by this warp: hand them back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[acc]);
+                    if (lane == 0) { mbar_arrive(&t_empty[acc]); mbar_arrive(&wd_empty[ws]); }
                 }
                 if (ok) {
 #pragma unroll
                     for (int x = 0; x < 16; x++) {
                         // kernUpdatedelta + kernAccSum (DevFunc.cu:490-507, 427-443); g/Mg as g*(1/Mg) (<= 1 ulp)
-                        const float ww = w[c + x];
-                        const float dd = mom * d[c + x] - lr * (g[x] * inv_mg + wc * ww);
+                        const float ww = w[x];
+                        const float dd = mom * d[x] - lr * (g[x] * inv_mg + wc * ww);
                         const float wn = dd + ww;
                         const size_t o = off0 + (size_t)(c + x) * Np;
                         st_stream_f32(W + o, wn);
@@ -245,7 +278,6 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                         Lo[o] = l;
                     }
                 }
-                if (has_next) load_wd16(Ln->W, Ln->D, noff0 + (size_t)c * Ln->Np, Ln->Np, nn < Ln->Np, w + c, d + c);
             }
             // bias gradient + bias update of the 128 units of this n-tile (kernAccSumrow, DevFunc.cu:267-285; BP_GPU.cu:434-437)
             if (tr.kt == 0 && half == 0 && n < L->N) {
@@ -267,6 +299,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
             }
             tr = nx;
         }
+        if (gp->dbg_progress && lane == 0) { gp->hang[8 + (blockIdx.x * 10 + warp) * 4 + 3] = 5000u; }
     }
     pdl_trigger();
     tc_fence_before();

@@ -47,6 +47,8 @@ using namespace ggd;
         if (_rc != GGD_OK) return _rc; \
     } while (0)
 
+constexpr int HANG_WORDS = 8 + 160 * 10 * 4;
+
 struct LayerInfo {
     int prev, cur;      // real units
     int Kp, Np;         // padded units (multiples of 64)
@@ -88,6 +90,7 @@ struct ggd_handle {
     bool persist;       // fused AND the bunch is one reduction tile: one persistent launch for all layers (dw_persist.cu)
     DwpArgs *dwp_dev;   // its argument block (device memory)
     unsigned int *dwp_counter;
+    unsigned int *hang_host, *hang_dev;   // host-mapped record written by a device-side watchdog before it traps
     cudaGraphExec_t g1, gN;
     int gN_steps;
     int launches_per_step;
@@ -251,6 +254,8 @@ static int build_plans(ggd_handle *h)
             d.b_hi = h->dwu[l].a_hi; d.b_lo = h->dwu[l].a_lo;   // activations below, box {64, 64}
             d.W = h->P + ly.w_off; d.D = h->Dl + ly.w_off; d.w_hi = h->Phi + ly.w_off; d.w_lo = h->Plo + ly.w_off;
             d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off;
+            GGD_TRY(make_tmap_2d(&d.w_map, d.W, 1, ly.Kp, ly.Np, ly.Np, 128, 32, 0));
+            GGD_TRY(make_tmap_2d(&d.d_map, d.D, 1, ly.Kp, ly.Np, ly.Np, 128, 32, 0));
             d.dx_hi = h->dx_hi[l]; d.dx_lo = h->dx_lo[l];
             d.Kp = ly.Kp; d.Np = ly.Np; d.N = ly.cur;
             d.k_tiles = ly.Kp / 64;
@@ -262,7 +267,8 @@ static int build_plans(ggd_handle *h)
         a.total_tiles = base;
         a.ctl = h->ctl; a.rows_per_bunch = h->M; a.M = h->M;
         a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
-        a.advance = 1; a.done_counter = h->dwp_counter;
+        a.advance = 1; a.done_counter = h->dwp_counter; a.hang = h->hang_dev;
+        { const char *ev = getenv("GGD_DWP_DEBUG"); a.dbg_progress = ev && atoi(ev) == 1; }
         GGD_CUDA(cudaMemcpy(h->dwp_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     }
     return GGD_OK;
@@ -582,6 +588,31 @@ static int upload(ggd_handle *h, const float *src, float *dst, size_t bytes)
     return GGD_OK;
 }
 
+// synchronise the main stream; a device-side watchdog trap is reported with its record (which barrier, block, iteration)
+static int sync_main(ggd_handle *h)
+{
+    static_assert(HANG_WORDS >= 8 + 160 * 10 * 4, "hang record");
+    cudaError_t e = cudaStreamSynchronize(h->s_main);
+    if (e == cudaSuccess) return GGD_OK;
+    const unsigned int *r = h->hang_host;
+    if (r && r[0] == 0xDEADu)
+    {
+        char buf[700]; int n = 0;
+        n += snprintf(buf + n, sizeof buf - n, "device pipeline watchdog: wait code %u gave up in block %u at iteration %u (parity %u, thread %u); waiters of that block [warp:code@it/parity]:", r[1], r[2], r[3], r[4], r[5]);
+        for (int w = 0; w < 10 && n < 600; w++) {
+            const unsigned int *q = r + 8 + (r[2] * 10 + w) * 4;
+            if (q[3]) n += snprintf(buf + n, sizeof buf - n, " %d:%u@%u/%u[%u]", w, q[0], q[1], q[2], q[3]);
+        }
+        int stuck = 0;
+        for (int b = 0; b < 160; b++) { bool any = false; for (int w = 0; w < 10; w++) any |= r[8 + (b * 10 + w) * 4 + 3] != 0; stuck += any; }
+        n += snprintf(buf + n, sizeof buf - n, "; blocks with waiters: %d", stuck);
+        set_error("%s: %s", buf, cudaGetErrorString(e));
+    }
+    else
+        set_error("cudaStreamSynchronize -> %s", cudaGetErrorString(e));
+    return GGD_ECUDA;
+}
+
 static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ)
 {
     const int nb = n_frames / h->M;   // trailing partial bunch dropped (BP_GPU.cu:173-180)
@@ -609,8 +640,8 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     }
     GGD_CUDA(cudaEventRecord(h->ev2, h->s_main));
     std::vector<double> tr(nb);
-    GGD_CUDA(cudaMemcpyAsync(tr.data(), h->trace, nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
-    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    if (cudaMemcpyAsync(tr.data(), h->trace, nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_main) != cudaSuccess) cudaGetLastError();
+    GGD_TRY(sync_main(h));
     float ms = 0;
     GGD_CUDA(cudaEventElapsedTime(&ms, h->ev1, h->ev2));
     h->stats.device_ms = ms;
@@ -705,6 +736,8 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     CK(cudaMalloc(&h->ctl, sizeof(StepCtl))); CK(cudaMemset(h->ctl, 0, sizeof(StepCtl)));
     CK(cudaMalloc(&h->dwp_dev, sizeof(DwpArgs))); CK(cudaMalloc(&h->dwp_counter, sizeof(unsigned int)));
     CK(cudaMemset(h->dwp_counter, 0, sizeof(unsigned int)));
+    CK(cudaHostAlloc(&h->hang_host, HANG_WORDS * sizeof(unsigned int), cudaHostAllocMapped)); memset(h->hang_host, 0, HANG_WORDS * sizeof(unsigned int));
+    CK(cudaHostGetDevicePointer(&h->hang_dev, h->hang_host, 0));
     // weights in: reference order (out + in*cur) -> padded pitch Np; then build the bf16 shadows with a zero-gradient-free pass
     for (int l = 1; l < h->L; l++) {
         const LayerInfo &ly = h->lay[l];
@@ -759,7 +792,7 @@ int ggd_destroy(ggd_handle *h)
         cudaFree(h->act_hi[l]); cudaFree(h->act_lo[l]); cudaFree(h->dx_hi[l]); cudaFree(h->dx_lo[l]);
         cudaFree(h->x32[l]); cudaFree(h->y32[l]); cudaFree(h->dy32[l]); cudaFree(h->dx32[l]);
     }
-    cudaFree(h->out32); cudaFree(h->alpha); cudaFree(h->colsum); cudaFree(h->ctl); cudaFree(h->dwp_dev); cudaFree(h->dwp_counter);
+    cudaFree(h->out32); cudaFree(h->alpha); cudaFree(h->colsum); cudaFree(h->ctl); cudaFree(h->dwp_dev); cudaFree(h->dwp_counter); if (h->hang_host) cudaFreeHost(h->hang_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
@@ -1040,7 +1073,7 @@ int ggd_profile_kernels(ggd_handle *h, int n_frames, const float *d_in, const fl
     if (h->tensor) { ProfScope ps(h, KC_SPLIT, h->s_main); launch_split_rows(d_in, nb * h->M, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main); }
     for (int b = 0; b < nb && rc == GGD_OK; b++) rc = enqueue_step(h, h->s_main, true, &launches);
     h->prof_on = false;
-    cudaStreamSynchronize(h->s_main);
+    if (rc == GGD_OK) rc = sync_main(h);
     for (size_t i = 0; i < h->prof_cls.size(); i++) {
         float ms = 0;
         cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]);
