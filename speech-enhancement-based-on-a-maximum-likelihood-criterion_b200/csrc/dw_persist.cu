@@ -5,21 +5,26 @@
 // Grid = one CTA per SM; every CTA owns a CONTIGUOUS range of the global tile list (layer, n-tile, k-tile; k fastest).
 // A tile is 128 output units n  x  64 input units k of one weight matrix:
 //     g[n][k] = sum_m dx[m][n] * y[m][k]        UMMA: M = 128 (n, TMEM lanes), N = 64 (k, TMEM columns), K = 128 frames
-// The operand roles are swapped with respect to dw_update.cu on purpose: a TMEM lane is an OUTPUT unit n, and n is the
-// contiguous index of the reference weight layout (W[k][n], index = out + in*cur).  The 32 lanes of an update warp
-// therefore address 32 consecutive floats of one W row: the fp32 weight / momentum / bf16-shadow traffic is fully
-// coalesced straight from registers, with no shared-memory transposition and no staging buffer.
+// A TMEM lane is an OUTPUT unit n, and n is the contiguous index of the reference weight layout (W[k][n], index =
+// out + in*cur), so a warp's 32 lanes work on 32 consecutive floats of one W row (conflict-free shared-memory rows).
 //
-// CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = update warps.
-//   * dx^T tile of the current n-tile (128 n x 128 frames, bf16 hi/lo, 64 KB) stays RESIDENT while the CTA walks the
-//     k-tiles; only the y^T tile (64 k x 128 frames, 32 KB) streams through a 2-stage ring.
-//   * the accumulator is double-buffered in TMEM (2 x 64 columns): the MMAs of tile t+1 run under the update of tile t.
-//   * the fp32 weights and momentum stream in by TMA as well (half tiles: 32 k x 128 n of W and of delta, 32 KB per
-//     stage, 3 stages = 1.5 tiles ahead of the update warps), so ~96 KB of HBM reads per SM are always in flight
-//     without holding a single register; the update warps read them conflict-free from shared memory (lane = n) and
-//     store W, delta and the bf16 shadows straight from registers: 16 B/param (+4 B/param of bf16 shadows).
-// The CTA that owns k-tile 0 of an n-tile also forms the bias gradient of those 128 units (column sums of dx over the
-// frames) and applies the bias update; the last CTA to finish advances the device-side bunch counter.
+// ALL global traffic is TMA; the SM's load/store units only touch shared memory:
+//   warp 0      producer: dx^T of the current n-tile (128 n x 128 frames bf16 hi/lo, 64 KB, resident while the CTA walks
+//               the k-tiles), y^T of the tile (64 k x 128 frames, 32 KB), and the fp32 weights + momentum in quarter
+//               tiles of 16 k rows (W and delta, 16 KB per stage, 5-stage ring) -- ~60 KB of HBM reads in flight per SM
+//               without holding a register;
+//   warp 1      TMEM allocator + single-thread tcgen05 MMA issuer (bf16x3), accumulator double-buffered in TMEM so the
+//               MMAs of tile t+1 run under the update of tile t;
+//   warps 2..9  update warps: every warp takes part in every ring stage (8 rows x 32 n each): gradient from TMEM,
+//               W / delta from shared memory, delta <- mom*delta - lr*(g/Mg + wc*W), W <- W + delta written back IN
+//               PLACE, bf16 hi/lo shadows into the stage's shadow buffers;
+//   warp 10     store warp: one TMA store per array and stage (W, delta, hi, lo), and it releases the stage to the
+//               producer once the store engine has read it;
+//   warp 11     bias warp: column sums of dx over the frames and the bias update for the n-tiles whose k-tile 0 belongs
+//               to this CTA (latency-bound L2 reads, hidden beside the tile pipeline).
+// Every consumer follows every ring stage in order: a parity wait cannot tell phase f from phase f+2, so no warp may
+// ever skip a stage (TMA loads land out of order).
+// HBM traffic: 16 B/param (+4 B/param of bf16 shadows).  The last CTA to finish advances the device-side bunch counter.
 #include "gemm_tc.cuh"
 #include "../../include/ggd_train.h"
 
@@ -33,13 +38,15 @@ constexpr int A_PART = 2 * A_HALF;                 // 16 KB: 128 n x 64 frames (
 constexpr int A_SLOT = KB * 2 * A_PART;            // 64 KB
 constexpr int B_PART = TK * BK * 2;                // 8 KB
 constexpr int B_STAGE = KB * 2 * B_PART;           // 32 KB
-constexpr int A_SLOTS = 1, B_STAGES = 2;
-constexpr int WD_ROWS = 32;                        // k rows per W/delta half-tile stage
-constexpr int WD_PART = WD_ROWS * TN * 4;          // 16 KB: 32 k x 128 n fp32
-constexpr int WD_STAGE = 2 * WD_PART;              // W then delta
-constexpr int WD_STAGES = 3;
-constexpr int SMEM = A_SLOTS * A_SLOT + B_STAGES * B_STAGE + WD_STAGES * WD_STAGE + 1024;
-constexpr int NTHREADS = 320;
+constexpr int WD_ROWS = 16;                        // k rows per ring stage (a quarter tile)
+constexpr int QUARTERS = TK / WD_ROWS;             // 4
+constexpr int WD_F32 = WD_ROWS * TN * 4;           // 8 KB: 16 k x 128 n fp32
+constexpr int WD_B16 = WD_ROWS * TN * 2;           // 4 KB
+constexpr int WD_STAGE = 2 * WD_F32 + 2 * WD_B16;  // W, delta, hi, lo = 24 KB
+constexpr int WD_LOAD = 2 * WD_F32;                // bytes that arrive by TMA per stage
+constexpr int WD_STAGES = 5;
+constexpr int SMEM = A_SLOT + B_STAGE + WD_STAGES * WD_STAGE + 1024;
+constexpr int NTHREADS = 384;
 constexpr int TMEM_COLS = 2 * TK;                  // double-buffered accumulator
 }  // namespace dwp
 
@@ -80,39 +87,60 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
         if (spins == (1u << 16) && rec && (threadIdx.x & 31) == 0) {   // note who is waiting on what, per warp
-            unsigned int *w = rec + 8 + (blockIdx.x * 10 + (threadIdx.x >> 5)) * 4;
-            w[0] = (unsigned int)code; w[1] = (unsigned int)it; w[2] = parity; w[3] |= 0x80000000u;
+            unsigned int *w = rec + 8 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 4;
+            w[0] = (unsigned int)code; w[1] = (unsigned int)it; w[2] = parity; w[3] = 1;
             __threadfence_system();
         }
         if (spins > (1u << 22)) hang_report(rec, code, it, parity);
     }
 }
 
-__device__ __forceinline__ void st_stream_f32(float *p, float v)
+// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v)
 {
-    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
+
+// TMA 2-D tiled store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpArgs *__restrict__ gp)
 {
     using namespace dwp;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *a_slots = smem, *b_ring = smem + A_SLOTS * A_SLOT, *wd_ring = b_ring + B_STAGES * B_STAGE;
-    __shared__ __align__(8) uint64_t a_full[A_SLOTS], a_empty[A_SLOTS], b_full[B_STAGES], b_empty[B_STAGES], t_full[2], t_empty[2];
-    __shared__ __align__(8) uint64_t wd_full[WD_STAGES], wd_empty[WD_STAGES];
+    uint8_t *a_slot = smem, *b_stage = smem + A_SLOT, *wd_ring = b_stage + B_STAGE;
+    __shared__ __align__(8) uint64_t a_full, a_empty, b_full, b_empty, t_full[2], t_empty[2];
+    __shared__ __align__(8) uint64_t wd_full[WD_STAGES], wd_done[WD_STAGES], wd_empty[WD_STAGES];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = gp->total_tiles;
     const int t0 = (int)((long long)T * blockIdx.x / gridDim.x), t1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
+    unsigned int *const hang = gp->hang;
 
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < A_SLOTS; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-            for (int s = 0; s < B_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+            mbar_init(&a_full, 1); mbar_init(&a_empty, 1); mbar_init(&b_full, 1); mbar_init(&b_empty, 1);
             for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
-            for (int s = 0; s < WD_STAGES; s++) { mbar_init(&wd_full[s], 1); mbar_init(&wd_empty[s], 8); }
+            for (int s = 0; s < WD_STAGES; s++) { mbar_init(&wd_full[s], 1); mbar_init(&wd_done[s], 8); mbar_init(&wd_empty[s], 1); }
             fence_mbar_init();
         }
         __syncwarp();
@@ -134,38 +162,34 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                 const DwpLayer *L = tr.L;
                 if (tr.key != key) {
                     key = tr.key;
-                    const int sl = a_cnt % A_SLOTS, ph = (a_cnt / A_SLOTS) & 1;
+                    mbar_wait_bounded(&a_empty, (a_cnt & 1) ^ 1, hang, 1, it);
                     a_cnt++;
-                    mbar_wait_bounded(&a_empty[sl], ph ^ 1, gp->hang, 1, it);
-                    mbar_expect_tx(&a_full[sl], A_SLOT);
-                    uint8_t *dst = a_slots + sl * A_SLOT;
+                    mbar_expect_tx(&a_full, A_SLOT);
 #pragma unroll
                     for (int kb = 0; kb < KB; kb++)
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
-                            tma_load_2d(dst + kb * 2 * A_PART + h * A_HALF, &L->a_hi, &a_full[sl], tr.nt * TN + 64 * h, kb * BK);
-                            tma_load_2d(dst + kb * 2 * A_PART + A_PART + h * A_HALF, &L->a_lo, &a_full[sl], tr.nt * TN + 64 * h, kb * BK);
+                            tma_load_2d(a_slot + kb * 2 * A_PART + h * A_HALF, &L->a_hi, &a_full, tr.nt * TN + 64 * h, kb * BK);
+                            tma_load_2d(a_slot + kb * 2 * A_PART + A_PART + h * A_HALF, &L->a_lo, &a_full, tr.nt * TN + 64 * h, kb * BK);
                         }
                 }
-                const int s = it % B_STAGES, ph = (it / B_STAGES) & 1;
-                mbar_wait_bounded(&b_empty[s], ph ^ 1, gp->hang, 2, it);
-                mbar_expect_tx(&b_full[s], B_STAGE);
-                uint8_t *dst = b_ring + s * B_STAGE;
+                mbar_wait_bounded(&b_empty, (it & 1) ^ 1, hang, 2, it);
+                mbar_expect_tx(&b_full, B_STAGE);
                 const int r0 = L->b_rows_from_ctl ? bunch_row0 : 0;
 #pragma unroll
                 for (int kb = 0; kb < KB; kb++) {
-                    tma_load_2d(dst + kb * 2 * B_PART, &L->b_hi, &b_full[s], tr.kt * TK, r0 + kb * BK);
-                    tma_load_2d(dst + kb * 2 * B_PART + B_PART, &L->b_lo, &b_full[s], tr.kt * TK, r0 + kb * BK);
+                    tma_load_2d(b_stage + kb * 2 * B_PART, &L->b_hi, &b_full, tr.kt * TK, r0 + kb * BK);
+                    tma_load_2d(b_stage + kb * 2 * B_PART + B_PART, &L->b_lo, &b_full, tr.kt * TK, r0 + kb * BK);
                 }
-                // fp32 weights / momentum of this tile: two half tiles of 32 k rows
+                // fp32 weights / momentum of this tile: four quarter tiles of 16 k rows
 #pragma unroll
-                for (int hs = 0; hs < 2; hs++) {
-                    const int seq = 2 * it + hs, ws = seq % WD_STAGES, wph = (seq / WD_STAGES) & 1;
-                    mbar_wait_bounded(&wd_empty[ws], wph ^ 1, gp->hang, 3, it);
-                    mbar_expect_tx(&wd_full[ws], WD_STAGE);
+                for (int qt = 0; qt < QUARTERS; qt++) {
+                    const int seq = QUARTERS * it + qt, ws = seq % WD_STAGES, wph = (seq / WD_STAGES) & 1;
+                    mbar_wait_bounded(&wd_empty[ws], wph ^ 1, hang, 3, it);
+                    mbar_expect_tx(&wd_full[ws], WD_LOAD);
                     uint8_t *wdst = wd_ring + ws * WD_STAGE;
-                    tma_load_2d(wdst, &L->w_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + hs * WD_ROWS);
-                    tma_load_2d(wdst + WD_PART, &L->d_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + hs * WD_ROWS);
+                    tma_load_2d(wdst, &L->w_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS);
+                    tma_load_2d(wdst + WD_F32, &L->d_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS);
                 }
             }
         }
@@ -174,21 +198,19 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
         if (lane == 0 && t0 < t1) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc = make_idesc_bf16(TN, TK, true, true);
-            int key = -1, a_cnt = 0, sl = 0;
+            int key = -1, a_cnt = 0;
             TileRef tr = decode_tile(gp, t0);
             for (int t = t0, it = 0; t < t1; t++, it++) {
                 if (tr.key != key) {
                     key = tr.key;
-                    sl = a_cnt % A_SLOTS;
-                    mbar_wait_bounded(&a_full[sl], (a_cnt / A_SLOTS) & 1, gp->hang, 4, it);
+                    mbar_wait_bounded(&a_full, a_cnt & 1, hang, 4, it);
                     a_cnt++;
                 }
-                const int s = it % B_STAGES;
-                mbar_wait_bounded(&b_full[s], (it / B_STAGES) & 1, gp->hang, 5, it);
+                mbar_wait_bounded(&b_full, it & 1, hang, 5, it);
                 const int acc = it & 1;
-                mbar_wait_bounded(&t_empty[acc], ((it >> 1) & 1) ^ 1, gp->hang, 6, it);
+                mbar_wait_bounded(&t_empty[acc], ((it >> 1) & 1) ^ 1, hang, 6, it);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(a_slots + sl * A_SLOT), b0 = smem_u32(b_ring + s * B_STAGE);
+                const uint32_t a0 = smem_u32(a_slot), b0 = smem_u32(b_stage);
                 const uint32_t d = tmem + acc * TK;
 #pragma unroll
                 for (int kb = 0; kb < KB; kb++) {
@@ -203,103 +225,137 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                         umma_bf16(d, dah, dbh, idesc, 1);
                     }
                 }
-                umma_commit(&b_empty[s]);
+                umma_commit(&b_empty);
                 umma_commit(&t_full[acc]);
                 TileRef nx = tr;
                 if (t + 1 < t1) nx = decode_tile(gp, t + 1);
-                if (t + 1 >= t1 || nx.key != key) umma_commit(&a_empty[sl]);   // last tile that reads this dx^T slot
+                if (t + 1 >= t1 || nx.key != key) umma_commit(&a_empty);   // last tile that reads this dx^T operand
                 tr = nx;
             }
         }
         __syncwarp();
+    } else if (warp == 10) {
+        if (lane == 0 && t0 < t1) {
+            // ===== store warp: TMA stores of finished stages; a stage goes back to the producer once it has been read =====
+            int prev_ws = -1;
+            for (int t = t0, it = 0; t < t1; t++, it++) {
+                const TileRef tr = decode_tile(gp, t);
+                const DwpLayer *L = tr.L;
+#pragma unroll
+                for (int qt = 0; qt < QUARTERS; qt++) {
+                    const int seq = QUARTERS * it + qt, ws = seq % WD_STAGES;
+                    mbar_wait_bounded(&wd_done[ws], (seq / WD_STAGES) & 1, hang, 10, it);
+                    const uint8_t *src = wd_ring + ws * WD_STAGE;
+                    const int c0 = tr.nt * TN, c1 = tr.kt * TK + qt * WD_ROWS;
+                    tma_store_2d(&L->w_map, src, c0, c1);
+                    tma_store_2d(&L->d_map, src + WD_F32, c0, c1);
+                    tma_store_2d(&L->hi_map, src + 2 * WD_F32, c0, c1);
+                    tma_store_2d(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1);
+                    tma_store_commit();
+                    if (prev_ws >= 0) {
+                        tma_store_wait_read<1>();            // everything but the newest group has left shared memory
+                        mbar_arrive(&wd_empty[prev_ws]);
+                    }
+                    prev_ws = ws;
+                }
+            }
+            tma_store_wait_all<0>();   // all writes performed before the CTA (and with it the grid) completes
+        }
+        __syncwarp();
+    } else if (warp == 11) {
+        // ===== bias warp: bias gradient + bias update of every n-tile whose k-tile 0 belongs to this CTA (kernAccSumrow,
+        // DevFunc.cu:267-285; BP_GPU.cu:434-437).  It only needs dx, so it runs beside the tile pipeline from the start;
+        // lane = 4 consecutive units, frames summed in ascending order like the reference.
+        const float mom = gp->mom, lr = gp->lr;
+        const int M = gp->M;
+        for (int t = t0; t < t1; t++) {
+            const TileRef tr = decode_tile(gp, t);
+            if (tr.kt != 0) continue;
+            const DwpLayer *L = tr.L;
+            const int Np = L->Np, n = tr.nt * TN + 4 * lane;
+            if (n >= Np) continue;
+            const bf16 *xh = L->dx_hi + n, *xl = L->dx_lo + n;
+            float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            int m = 0;
+            for (; m + 8 <= M; m += 8) {
+                uint2 vh[8], vl[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    vh[u] = *reinterpret_cast<const uint2 *>(xh + (size_t)(m + u) * Np);
+                    vl[u] = *reinterpret_cast<const uint2 *>(xl + (size_t)(m + u) * Np);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    s[0] += __uint_as_float(vh[u].x << 16) + __uint_as_float(vl[u].x << 16);
+                    s[1] += __uint_as_float(vh[u].x & 0xFFFF0000u) + __uint_as_float(vl[u].x & 0xFFFF0000u);
+                    s[2] += __uint_as_float(vh[u].y << 16) + __uint_as_float(vl[u].y << 16);
+                    s[3] += __uint_as_float(vh[u].y & 0xFFFF0000u) + __uint_as_float(vl[u].y & 0xFFFF0000u);
+                }
+            }
+            for (; m < M; m++) {
+                const uint2 vh = *reinterpret_cast<const uint2 *>(xh + (size_t)m * Np), vl = *reinterpret_cast<const uint2 *>(xl + (size_t)m * Np);
+                s[0] += __uint_as_float(vh.x << 16) + __uint_as_float(vl.x << 16);
+                s[1] += __uint_as_float(vh.x & 0xFFFF0000u) + __uint_as_float(vl.x & 0xFFFF0000u);
+                s[2] += __uint_as_float(vh.y << 16) + __uint_as_float(vl.y << 16);
+                s[3] += __uint_as_float(vh.y & 0xFFFF0000u) + __uint_as_float(vl.y & 0xFFFF0000u);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (n + c < L->N) {
+                    const float db = mom * L->db[n + c] - lr * (s[c] / gp->Mg);   // no weight cost on biases (BP_GPU.cu:435)
+                    L->db[n + c] = db;
+                    L->b[n + c] = db + L->b[n + c];
+                }
+            }
+        }
     } else if (t0 < t1) {
-        // ===== update warps (8): quadrant q = lanes [32q, 32q+32) of the accumulator, `half` = 32 of its 64 columns =====
-        const int e = warp - 2, q = warp & 3, half = e >> 2;
+        // ===== update warps (8): quadrant q = accumulator lanes [32q, 32q+32); `h` = which 8 of a stage's 16 rows =====
+        const int e = warp - 2, q = warp & 3, h = e >> 2;
         const float mom = gp->mom, lr = gp->lr, inv_mg = 1.0f / gp->Mg;
         TileRef tr = decode_tile(gp, t0);
         for (int t = t0, it = 0; t < t1; t++, it++) {
             const DwpLayer *L = tr.L;
-            float *W = L->W, *D = L->D;
-            bf16 *Hi = L->w_hi, *Lo = L->w_lo;
-            const int Np = L->Np;
             const float wc = L->wc;
-            const int n = tr.nt * TN + q * 32 + lane;
-            const bool ok = n < Np;
-            const size_t off0 = (size_t)(tr.kt * TK + half * 32) * Np + n;
-            TileRef nx = tr;
-            if (t + 1 < t1) nx = decode_tile(gp, t + 1);
-
-            if (gp->dbg_progress && lane == 0) { gp->hang[8 + (blockIdx.x * 10 + warp) * 4 + 3] = 1000u + (unsigned int)it; }
             const int acc = it & 1;
-            // Every update warp follows EVERY stage of the W/delta ring in order (full -> empty), although it only reads
-            // the half tile of its own `half`: a warp that skipped the other half's stages could get two phases away from
-            // a barrier (TMA loads land out of order) and a parity wait cannot tell phase f from phase f+2.
-            const int seq = 2 * it + half, ws = seq % WD_STAGES;
-            const int oseq = 2 * it + (half ^ 1), ows = oseq % WD_STAGES;
-            const float *ws_w = reinterpret_cast<const float *>(wd_ring + ws * WD_STAGE) + q * 32 + lane;
-            const float *ws_d = ws_w + WD_PART / 4;
-            if (half == 0) {
-                mbar_wait_bounded(&wd_full[ws], (seq / WD_STAGES) & 1, gp->hang, 7, it);
-                mbar_wait_bounded(&wd_full[ows], (oseq / WD_STAGES) & 1, gp->hang, 9, it);
-            } else {
-                mbar_wait_bounded(&wd_full[ows], (oseq / WD_STAGES) & 1, gp->hang, 9, it);
-                mbar_wait_bounded(&wd_full[ws], (seq / WD_STAGES) & 1, gp->hang, 7, it);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&wd_empty[ows]);   // not read by this warp
-            mbar_wait_bounded(&t_full[acc], (it >> 1) & 1, gp->hang, 8, it);
+            mbar_wait_bounded(&t_full[acc], (it >> 1) & 1, hang, 8, it);
             __syncwarp();
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * TK + half * 32;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * TK + h * 8;
 #pragma unroll
-            for (int c = 0; c < 32; c += 16) {
-                float g[16], w[16], d[16];
-#pragma unroll
-                for (int x = 0; x < 16; x++) { w[x] = ws_w[(c + x) * TN]; d[x] = ws_d[(c + x) * TN]; }
-                tmem_ld16(taddr + c, g);
-                if (c == 16) {   // accumulator and W/delta stage have been drained by this warp: hand them back
+            for (int qt = 0; qt < QUARTERS; qt++) {
+                const int seq = QUARTERS * it + qt, ws = seq % WD_STAGES;
+                uint8_t *st = wd_ring + ws * WD_STAGE;
+                float *sw = reinterpret_cast<float *>(st) + (h * 8) * TN + q * 32 + lane;
+                float *sd = sw + WD_F32 / 4;
+                bf16 *shi = reinterpret_cast<bf16 *>(st + 2 * WD_F32) + (h * 8) * TN + q * 32 + lane;
+                bf16 *slo = shi + WD_B16 / 2;
+                float g[8];
+                tmem_ld8(taddr + qt * WD_ROWS, g);
+                if (qt == QUARTERS - 1) {   // the accumulator has been drained by this warp: hand it back to the MMA issuer
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(&t_empty[acc]); mbar_arrive(&wd_empty[ws]); }
+                    if (lane == 0) mbar_arrive(&t_empty[acc]);
                 }
-                if (ok) {
+                mbar_wait_bounded(&wd_full[ws], (seq / WD_STAGES) & 1, hang, 7, it);
 #pragma unroll
-                    for (int x = 0; x < 16; x++) {
-                        // kernUpdatedelta + kernAccSum (DevFunc.cu:490-507, 427-443); g/Mg as g*(1/Mg) (<= 1 ulp)
-                        const float ww = w[x];
-                        const float dd = mom * d[x] - lr * (g[x] * inv_mg + wc * ww);
-                        const float wn = dd + ww;
-                        const size_t o = off0 + (size_t)(c + x) * Np;
-                        st_stream_f32(W + o, wn);
-                        st_stream_f32(D + o, dd);
-                        bf16 h, l;
-                        split_bf16(wn, h, l);
-                        Hi[o] = h;
-                        Lo[o] = l;
-                    }
+                for (int x = 0; x < 8; x++) {
+                    // kernUpdatedelta + kernAccSum (DevFunc.cu:490-507, 427-443); g/Mg as g*(1/Mg) (<= 1 ulp)
+                    const float ww = sw[x * TN];
+                    const float dd = mom * sd[x * TN] - lr * (g[x] * inv_mg + wc * ww);
+                    const float wn = dd + ww;
+                    sw[x * TN] = wn;
+                    sd[x * TN] = dd;
+                    bf16 hv, lv;
+                    split_bf16(wn, hv, lv);
+                    shi[x * TN] = hv;
+                    slo[x * TN] = lv;
                 }
+                fence_async_proxy();      // the stage is read by the TMA store engine next
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wd_done[ws]);
             }
-            // bias gradient + bias update of the 128 units of this n-tile (kernAccSumrow, DevFunc.cu:267-285; BP_GPU.cu:434-437)
-            if (tr.kt == 0 && half == 0 && n < L->N) {
-                const bf16 *xh = L->dx_hi + n, *xl = L->dx_lo + n;
-                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-                const int M = gp->M;
-                int m = 0;
-                for (; m + 4 <= M; m += 4) {
-                    s0 += join_bf16(xh[(size_t)m * Np], xl[(size_t)m * Np]);
-                    s1 += join_bf16(xh[(size_t)(m + 1) * Np], xl[(size_t)(m + 1) * Np]);
-                    s2 += join_bf16(xh[(size_t)(m + 2) * Np], xl[(size_t)(m + 2) * Np]);
-                    s3 += join_bf16(xh[(size_t)(m + 3) * Np], xl[(size_t)(m + 3) * Np]);
-                }
-                for (; m < M; m++) s0 += join_bf16(xh[(size_t)m * Np], xl[(size_t)m * Np]);
-                const float sum = (s0 + s1) + (s2 + s3);
-                const float db = mom * L->db[n] - lr * (sum / gp->Mg);   // no weight cost on biases (BP_GPU.cu:435)
-                L->db[n] = db;
-                L->b[n] = db + L->b[n];
-            }
-            tr = nx;
+            if (t + 1 < t1) tr = decode_tile(gp, t + 1);
         }
-        if (gp->dbg_progress && lane == 0) { gp->hang[8 + (blockIdx.x * 10 + warp) * 4 + 3] = 5000u; }
     }
     pdl_trigger();
     tc_fence_before();

@@ -87,7 +87,8 @@ int dw_update_init();
 struct DwpLayer {
     CUtensorMap a_hi, a_lo;   // dE/dx of this layer, bf16 [Mp][Np], box {64 units, 64 frames}
     CUtensorMap b_hi, b_lo;   // activations of the layer below (chunk input for layer 1), bf16 [rows][Kp], box {64, 64}
-    CUtensorMap w_map, d_map; // fp32 weights / momentum [Kp][Np], box {128 n, 32 k}, no swizzle
+    CUtensorMap w_map, d_map; // fp32 weights / momentum [Kp][Np], box {128 n, 16 k}, no swizzle (TMA load AND store)
+    CUtensorMap hi_map, lo_map;  // bf16 shadows [Kp][Np], box {128 n, 16 k}, no swizzle (TMA store)
     float *W, *D;             // fp32 weights / momentum [Kp][Np]
     bf16 *w_hi, *w_lo;        // shadows [Kp][Np]
     float *b, *db;            // bias and its momentum
@@ -107,7 +108,6 @@ struct DwpArgs {
     float mom, lr, Mg;
     int advance;                  // last CTA out increments ctl->bunch_idx
     unsigned int *done_counter;
-    int dbg_progress;             // GGD_DWP_DEBUG=1: update warps stamp their loop position into `hang` (slow; debugging only)
     unsigned int *hang;           // host-mapped [8]: filled by a waiter that gave up (see mbar_wait_bounded)
 };
 int launch_dw_persist(const DwpArgs *dev_args, int grid, cudaStream_t s);

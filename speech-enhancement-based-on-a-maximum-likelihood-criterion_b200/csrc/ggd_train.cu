@@ -47,7 +47,7 @@ using namespace ggd;
         if (_rc != GGD_OK) return _rc; \
     } while (0)
 
-constexpr int HANG_WORDS = 8 + 160 * 10 * 4;
+constexpr int HANG_WORDS = 8 + 160 * 12 * 4;
 
 struct LayerInfo {
     int prev, cur;      // real units
@@ -254,8 +254,10 @@ static int build_plans(ggd_handle *h)
             d.b_hi = h->dwu[l].a_hi; d.b_lo = h->dwu[l].a_lo;   // activations below, box {64, 64}
             d.W = h->P + ly.w_off; d.D = h->Dl + ly.w_off; d.w_hi = h->Phi + ly.w_off; d.w_lo = h->Plo + ly.w_off;
             d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off;
-            GGD_TRY(make_tmap_2d(&d.w_map, d.W, 1, ly.Kp, ly.Np, ly.Np, 128, 32, 0));
-            GGD_TRY(make_tmap_2d(&d.d_map, d.D, 1, ly.Kp, ly.Np, ly.Np, 128, 32, 0));
+            GGD_TRY(make_tmap_2d(&d.w_map, d.W, 1, ly.Kp, ly.Np, ly.Np, 128, 16, 0));
+            GGD_TRY(make_tmap_2d(&d.d_map, d.D, 1, ly.Kp, ly.Np, ly.Np, 128, 16, 0));
+            GGD_TRY(make_tmap_2d(&d.hi_map, d.w_hi, 0, ly.Kp, ly.Np, ly.Np, 128, 16, 0));
+            GGD_TRY(make_tmap_2d(&d.lo_map, d.w_lo, 0, ly.Kp, ly.Np, ly.Np, 128, 16, 0));
             d.dx_hi = h->dx_hi[l]; d.dx_lo = h->dx_lo[l];
             d.Kp = ly.Kp; d.Np = ly.Np; d.N = ly.cur;
             d.k_tiles = ly.Kp / 64;
@@ -268,7 +270,6 @@ static int build_plans(ggd_handle *h)
         a.ctl = h->ctl; a.rows_per_bunch = h->M; a.M = h->M;
         a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
         a.advance = 1; a.done_counter = h->dwp_counter; a.hang = h->hang_dev;
-        { const char *ev = getenv("GGD_DWP_DEBUG"); a.dbg_progress = ev && atoi(ev) == 1; }
         GGD_CUDA(cudaMemcpy(h->dwp_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     }
     return GGD_OK;
@@ -591,7 +592,7 @@ static int upload(ggd_handle *h, const float *src, float *dst, size_t bytes)
 // synchronise the main stream; a device-side watchdog trap is reported with its record (which barrier, block, iteration)
 static int sync_main(ggd_handle *h)
 {
-    static_assert(HANG_WORDS >= 8 + 160 * 10 * 4, "hang record");
+    static_assert(HANG_WORDS >= 8 + 160 * 12 * 4, "hang record");
     cudaError_t e = cudaStreamSynchronize(h->s_main);
     if (e == cudaSuccess) return GGD_OK;
     const unsigned int *r = h->hang_host;
@@ -599,12 +600,12 @@ static int sync_main(ggd_handle *h)
     {
         char buf[700]; int n = 0;
         n += snprintf(buf + n, sizeof buf - n, "device pipeline watchdog: wait code %u gave up in block %u at iteration %u (parity %u, thread %u); waiters of that block [warp:code@it/parity]:", r[1], r[2], r[3], r[4], r[5]);
-        for (int w = 0; w < 10 && n < 600; w++) {
-            const unsigned int *q = r + 8 + (r[2] * 10 + w) * 4;
+        for (int w = 0; w < 12 && n < 600; w++) {
+            const unsigned int *q = r + 8 + (r[2] * 12 + w) * 4;
             if (q[3]) n += snprintf(buf + n, sizeof buf - n, " %d:%u@%u/%u[%u]", w, q[0], q[1], q[2], q[3]);
         }
         int stuck = 0;
-        for (int b = 0; b < 160; b++) { bool any = false; for (int w = 0; w < 10; w++) any |= r[8 + (b * 10 + w) * 4 + 3] != 0; stuck += any; }
+        for (int b = 0; b < 160; b++) { bool any = false; for (int w = 0; w < 12; w++) any |= r[8 + (b * 12 + w) * 4 + 3] != 0; stuck += any; }
         n += snprintf(buf + n, sizeof buf - n, "; blocks with waiters: %d", stuck);
         set_error("%s: %s", buf, cudaGetErrorString(e));
     }
