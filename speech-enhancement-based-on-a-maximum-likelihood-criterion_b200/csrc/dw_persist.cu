@@ -115,6 +115,33 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *s
                  ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// L2 cache policies: the fp32 master weights / momentum are touched once per step (evict first); the bf16 shadows are
+// re-read by the forward and backward GEMMs of the next step and fit the 126 MB L2 (evict last).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *m, const void *smem_src, int c0, int c1, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -157,6 +184,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
         if (lane == 0 && t0 < t1) {
             // ===== TMA producer =====
             int key = -1, a_cnt = 0;
+            const uint64_t pol_stream = l2_policy_evict_first();
             for (int t = t0, it = 0; t < t1; t++, it++) {
                 const TileRef tr = decode_tile(gp, t);
                 const DwpLayer *L = tr.L;
@@ -188,8 +216,13 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                     mbar_wait_bounded(&wd_empty[ws], wph ^ 1, hang, 3, it);
                     mbar_expect_tx(&wd_full[ws], WD_LOAD);
                     uint8_t *wdst = wd_ring + ws * WD_STAGE;
-                    tma_load_2d(wdst, &L->w_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS);
-                    tma_load_2d(wdst + WD_F32, &L->d_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS);
+                    if (gp->l2_hints) {
+                        tma_load_2d_hint(wdst, &L->w_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS, pol_stream);
+                        tma_load_2d_hint(wdst + WD_F32, &L->d_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS, pol_stream);
+                    } else {
+                        tma_load_2d(wdst, &L->w_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS);
+                        tma_load_2d(wdst + WD_F32, &L->d_map, &wd_full[ws], tr.nt * TN, tr.kt * TK + qt * WD_ROWS);
+                    }
                 }
             }
         }
@@ -238,6 +271,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
         if (lane == 0 && t0 < t1) {
             // ===== store warp: TMA stores of finished stages; a stage goes back to the producer once it has been read =====
             int prev_ws = -1;
+            const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
             for (int t = t0, it = 0; t < t1; t++, it++) {
                 const TileRef tr = decode_tile(gp, t);
                 const DwpLayer *L = tr.L;
@@ -247,10 +281,17 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                     mbar_wait_bounded(&wd_done[ws], (seq / WD_STAGES) & 1, hang, 10, it);
                     const uint8_t *src = wd_ring + ws * WD_STAGE;
                     const int c0 = tr.nt * TN, c1 = tr.kt * TK + qt * WD_ROWS;
-                    tma_store_2d(&L->w_map, src, c0, c1);
-                    tma_store_2d(&L->d_map, src + WD_F32, c0, c1);
-                    tma_store_2d(&L->hi_map, src + 2 * WD_F32, c0, c1);
-                    tma_store_2d(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1);
+                    if (gp->l2_hints) {
+                        tma_store_2d_hint(&L->w_map, src, c0, c1, pol_stream);
+                        tma_store_2d_hint(&L->d_map, src + WD_F32, c0, c1, pol_stream);
+                        tma_store_2d_hint(&L->hi_map, src + 2 * WD_F32, c0, c1, pol_keep);
+                        tma_store_2d_hint(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1, pol_keep);
+                    } else {
+                        tma_store_2d(&L->w_map, src, c0, c1);
+                        tma_store_2d(&L->d_map, src + WD_F32, c0, c1);
+                        tma_store_2d(&L->hi_map, src + 2 * WD_F32, c0, c1);
+                        tma_store_2d(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1);
+                    }
                     tma_store_commit();
                     if (prev_ws >= 0) {
                         tma_store_wait_read<1>();            // everything but the newest group has left shared memory

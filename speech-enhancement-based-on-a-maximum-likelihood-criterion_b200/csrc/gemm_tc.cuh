@@ -108,6 +108,7 @@ struct DwpArgs {
     float mom, lr, Mg;
     int advance;                  // last CTA out increments ctl->bunch_idx
     unsigned int *done_counter;
+    int l2_hints;                 // evict-first fp32 streams, evict-last shadows (GGD_L2_HINTS, default 1)
     unsigned int *hang;           // host-mapped [8]: filled by a waiter that gave up (see mbar_wait_bounded)
 };
 int launch_dw_persist(const DwpArgs *dev_args, int grid, cudaStream_t s);

@@ -270,6 +270,7 @@ static int build_plans(ggd_handle *h)
         a.ctl = h->ctl; a.rows_per_bunch = h->M; a.M = h->M;
         a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
         a.advance = 1; a.done_counter = h->dwp_counter; a.hang = h->hang_dev;
+        { const char *ev = getenv("GGD_L2_HINTS"); a.l2_hints = !(ev && atoi(ev) == 0); }
         GGD_CUDA(cudaMemcpy(h->dwp_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     }
     return GGD_OK;
