@@ -26,6 +26,7 @@
 // ever skip a stage (TMA loads land out of order).
 // HBM traffic: 16 B/param (+4 B/param of bf16 shadows).  The last CTA to finish advances the device-side bunch counter.
 #include "gemm_tc.cuh"
+#include "pipe.cuh"
 #include "../../include/ggd_train.h"
 
 namespace ggd {
@@ -68,85 +69,6 @@ __device__ __forceinline__ TileRef decode_tile(const DwpArgs *gp, int t)
     tr.key = (l << 16) | tr.nt;
     return tr;
 }
-
-// Bounded mbarrier wait: a pipeline bug must surface as an error, never as a hung GPU.  After ~2^22 failed probes
-// (seconds) the waiter records {code, block, iteration, parity} in host-mapped memory and traps.
-__device__ __noinline__ void hang_report(unsigned int *rec, int code, int it, uint32_t parity)
-{
-    if (rec) {
-        rec[1] = (unsigned int)code; rec[2] = blockIdx.x; rec[3] = (unsigned int)it; rec[4] = parity; rec[5] = threadIdx.x;
-        __threadfence_system();
-        rec[0] = 0xDEADu;
-        __threadfence_system();
-    }
-    __trap();
-}
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, unsigned int *rec, int code, int it)
-{
-    unsigned int spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        ++spins;
-        if (spins == (1u << 16) && rec && (threadIdx.x & 31) == 0) {   // note who is waiting on what, per warp
-            unsigned int *w = rec + 8 + (blockIdx.x * 12 + (threadIdx.x >> 5)) * 4;
-            w[0] = (unsigned int)code; w[1] = (unsigned int)it; w[2] = parity; w[3] = 1;
-            __threadfence_system();
-        }
-        if (spins > (1u << 22)) hang_report(rec, code, it, parity);
-    }
-}
-
-// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v)
-{
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
-}
-
-// TMA 2-D tiled store shared -> global (bulk async-group completion)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-// L2 cache policies: the fp32 master weights / momentum are touched once per step (evict first); the bf16 shadows are
-// re-read by the forward and backward GEMMs of the next step and fit the 126 MB L2 (evict last).
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, uint64_t pol)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *m, const void *smem_src, int c0, int c1, uint64_t pol)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
-                 ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpArgs *__restrict__ gp)
 {

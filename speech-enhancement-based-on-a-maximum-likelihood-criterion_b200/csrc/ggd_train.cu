@@ -11,6 +11,7 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "dp_update.cuh"
+#include "dp_push.cuh"
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -102,6 +103,14 @@ struct ggd_handle {
     void *peer_base[5][DP_MAX_RANKS];   // IPC-mapped peer allocations (G, Phi, Plo, P, flags)
     unsigned int *dp_flags, *dp_counters;   // local: per layer [2][DP_MAX_RANKS] arrival flags; per layer {step, blocks}, then {error}
     int dp_overlap;     // 0 (default): one allreduce at the end; 1: per-layer allreduce + update on the communication stream
+    // push-model data parallelism (dp_push.cuh): gradient tiles pushed to their owners, shadows pushed back, no NCCL on the step
+    bool dp_push;
+    DpxArgs *dpx_dev;
+    float *px_rbuf, *px_bias, *px_asum;          // receive slots: gradient tiles, bias partials, sum|e|^beta partials
+    unsigned int *px_flags, *px_counters;         // flags (written by peers), {step, k1_done, k2_done, error}
+    void *px_peer[7][DPX_MAX];                    // IPC-mapped: rbuf, bias, asum, flags, Phi, Plo, P
+    int px_own_begin[DPX_MAX + 1], px_slot_tiles, px_total_tiles, px_k2_smem, px_k2_stages, px_k2_stage_bytes;
+    float **px_peerP_dev; long long *px_woff_dev;
     // host mirrors / stats
     std::vector<float> losses;
     std::vector<float> h_out;
@@ -127,6 +136,7 @@ struct ProfScope {
 };
 
 static int dp_p2p_setup(ggd_handle *h);
+static int build_dpx(ggd_handle *h);
 
 static void free_chunk(ggd_handle *h)
 {
@@ -273,6 +283,7 @@ static int build_plans(ggd_handle *h)
         { const char *ev = getenv("GGD_L2_HINTS"); a.l2_hints = !(ev && atoi(ev) == 0); }
         GGD_CUDA(cudaMemcpy(h->dwp_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     }
+    if (h->dp_push) GGD_TRY(build_dpx(h));
     return GGD_OK;
 }
 
@@ -382,6 +393,120 @@ static int dp_p2p_gather_master(ggd_handle *h)
     return GGD_OK;
 }
 
+// ---- push-model data parallelism: buffers, IPC exchange, tile ownership ---------------------------------------------
+static int ipc_exchange(ggd_handle *h, void *const *local, int nbuf, void *(*peer)[DPX_MAX])
+{
+    const int world = h->cfg.world_size, rank = h->cfg.rank;
+    std::vector<cudaIpcMemHandle_t> mine(nbuf), all((size_t)nbuf * world);
+    for (int k = 0; k < nbuf; k++) GGD_CUDA(cudaIpcGetMemHandle(&mine[k], local[k]));
+    cudaIpcMemHandle_t *d_all = nullptr, *d_mine = nullptr;
+    const size_t bytes = sizeof(cudaIpcMemHandle_t) * nbuf;
+    GGD_CUDA(cudaMalloc(&d_all, bytes * world));
+    GGD_CUDA(cudaMalloc(&d_mine, bytes));
+    GGD_CUDA(cudaMemcpy(d_mine, mine.data(), bytes, cudaMemcpyHostToDevice));
+    GGD_NCCL(ncclAllGather(d_mine, d_all, bytes, ncclChar, h->comm, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    GGD_CUDA(cudaMemcpy(all.data(), d_all, bytes * world, cudaMemcpyDeviceToHost));
+    cudaFree(d_all); cudaFree(d_mine);
+    for (int p = 0; p < world; p++)
+        for (int k = 0; k < nbuf; k++) {
+            if (p == rank) { peer[k][p] = local[k]; continue; }
+            cudaError_t e = cudaIpcOpenMemHandle(&peer[k][p], all[(size_t)p * nbuf + k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d, buffer %d): %s", p, k, cudaGetErrorString(e)); return GGD_ECUDA; }
+        }
+    return GGD_OK;
+}
+
+static int dp_barrier(ggd_handle *h)
+{
+    GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
+    GGD_CUDA(cudaStreamSynchronize(h->s_main));
+    return GGD_OK;
+}
+
+static int dp_push_setup(ggd_handle *h)
+{
+    const int world = h->cfg.world_size, L = h->L, D = h->units[L - 1];
+    int total = 0;
+    for (int l = 1; l < L; l++) total += ceil_div(h->lay[l].Np, 128) * (h->lay[l].Kp / 64);
+    h->px_total_tiles = total;
+    h->px_slot_tiles = 1;
+    for (int o = 0; o <= world; o++) h->px_own_begin[o] = (int)((long long)total * o / world);
+    for (int o = 0; o < world; o++) h->px_slot_tiles = std::max(h->px_slot_tiles, h->px_own_begin[o + 1] - h->px_own_begin[o]);
+    const size_t rb = (size_t)world * h->px_slot_tiles * 8192, bb = (size_t)world * h->nbias, ab = (size_t)world * D;
+    GGD_CUDA(cudaMalloc(&h->px_rbuf, rb * sizeof(float)));   GGD_CUDA(cudaMemset(h->px_rbuf, 0, rb * sizeof(float)));
+    GGD_CUDA(cudaMalloc(&h->px_bias, bb * sizeof(float)));   GGD_CUDA(cudaMemset(h->px_bias, 0, bb * sizeof(float)));
+    GGD_CUDA(cudaMalloc(&h->px_asum, ab * sizeof(float)));   GGD_CUDA(cudaMemset(h->px_asum, 0, ab * sizeof(float)));
+    GGD_CUDA(cudaMalloc(&h->px_flags, DPX_FLAG_WORDS * sizeof(unsigned int)));
+    GGD_CUDA(cudaMemset(h->px_flags, 0, DPX_FLAG_WORDS * sizeof(unsigned int)));
+    GGD_CUDA(cudaMalloc(&h->px_counters, 8 * sizeof(unsigned int)));
+    GGD_CUDA(cudaMemset(h->px_counters, 0, 8 * sizeof(unsigned int)));
+    GGD_CUDA(cudaMalloc(&h->dpx_dev, sizeof(DpxArgs)));
+    void *local[7] = {h->px_rbuf, h->px_bias, h->px_asum, h->px_flags, h->Phi, h->Plo, h->P};
+    GGD_TRY(ipc_exchange(h, local, 7, h->px_peer));
+    h->px_k2_smem = dp_push_k2_smem(world, &h->px_k2_stages, &h->px_k2_stage_bytes);
+    GGD_TRY(dp_push_init());
+    std::vector<float *> pp(DPX_MAX, nullptr);
+    std::vector<long long> wo(GGD_MAXLAYER, 0);
+    for (int p = 0; p < world; p++) pp[p] = (float *)h->px_peer[6][p];
+    for (int l = 1; l < L; l++) wo[l - 1] = (long long)h->lay[l].w_off;
+    GGD_CUDA(cudaMalloc(&h->px_peerP_dev, DPX_MAX * sizeof(float *)));
+    GGD_CUDA(cudaMalloc(&h->px_woff_dev, GGD_MAXLAYER * sizeof(long long)));
+    GGD_CUDA(cudaMemcpy(h->px_peerP_dev, pp.data(), DPX_MAX * sizeof(float *), cudaMemcpyHostToDevice));
+    GGD_CUDA(cudaMemcpy(h->px_woff_dev, wo.data(), GGD_MAXLAYER * sizeof(long long), cudaMemcpyHostToDevice));
+    h->dp_push = true;
+    GGD_TRY(dp_barrier(h));    // nobody may enter the first step before every rank has mapped everyone
+    return GGD_OK;
+}
+
+// argument block of the push kernels (needs the chunk buffers: rebuilt with the plans)
+static int build_dpx(ggd_handle *h)
+{
+    const int world = h->cfg.world_size, rank = h->cfg.rank, L = h->L;
+    DpxArgs *a = new DpxArgs();
+    memset(a, 0, sizeof *a);
+    int base = 0, boff = 0;
+    for (int l = 1; l < L; l++) {
+        const LayerInfo &ly = h->lay[l];
+        DpxLayer &d = a->layer[a->nlayers++];
+        d.a_hi = h->dwu[l].b_hi; d.a_lo = h->dwu[l].b_lo;
+        d.b_hi = h->dwu[l].a_hi; d.b_lo = h->dwu[l].a_lo;
+        int rc;
+        if ((rc = make_tmap_2d(&d.w_map, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
+        if ((rc = make_tmap_2d(&d.d_map, h->Dl + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
+        for (int p = 0; p < world; p++) {
+            if ((rc = make_tmap_2d(&d.hi_map[p], (bf16 *)h->px_peer[4][p] + ly.w_off, 0, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
+            if ((rc = make_tmap_2d(&d.lo_map[p], (bf16 *)h->px_peer[5][p] + ly.w_off, 0, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
+        }
+        d.dx_hi = h->dx_hi[l]; d.dx_lo = h->dx_lo[l];
+        d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off;
+        d.Kp = ly.Kp; d.Np = ly.Np; d.N = ly.cur; d.k_tiles = ly.Kp / 64; d.tile_base = base;
+        d.b_rows_from_ctl = (l == 1); d.bias_off = boff; d.wc = h->cfg.weightcost;
+        base += ceil_div(ly.Np, 128) * d.k_tiles;
+        boff += ly.Np;
+    }
+    const long long slot_rows = (long long)h->px_slot_tiles * 64;
+    for (int p = 0; p < world; p++) {
+        int rc;
+        // rank p's receive slot for MY tiles (source index = my rank), and my own slot holding source p's tiles
+        if ((rc = make_tmap_2d(&a->push_map[p], (float *)h->px_peer[0][p] + (size_t)rank * slot_rows * 128, 1, slot_rows, 128, 128, 128, 16, 0))) { delete a; return rc; }
+        if ((rc = make_tmap_2d(&a->part_map[p], h->px_rbuf + (size_t)p * slot_rows * 128, 1, slot_rows, 128, 128, 128, 8, 0))) { delete a; return rc; }
+        a->bias_slot[p] = (float *)h->px_peer[1][p];
+        a->asum_slot[p] = (float *)h->px_peer[2][p];
+        a->flags[p] = (unsigned int *)h->px_peer[3][p];
+    }
+    a->counters = h->px_counters; a->error_flag = h->px_counters + 4; a->hang = h->hang_dev; a->ctl = h->ctl;
+    for (int o = 0; o <= world; o++) a->own_begin[o] = h->px_own_begin[o];
+    a->total_tiles = h->px_total_tiles; a->world = world; a->rank = rank; a->nbias = (int)h->nbias;
+    a->rows_per_bunch = h->M; a->M = h->M;
+    a->k2_stages = h->px_k2_stages; a->k2_stage_bytes = h->px_k2_stage_bytes;
+    a->mom = h->cfg.momentum; a->lr = h->cfg.lrate; a->Mg = (float)h->Mg;
+    cudaError_t e = cudaMemcpy(h->dpx_dev, a, sizeof *a, cudaMemcpyHostToDevice);
+    delete a;
+    GGD_CUDA(e);
+    return GGD_OK;
+}
+
 // ---- one training step (forward, loss gradient, backward, update); stream-ordered, no host sync ----
 static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches)
 {
@@ -414,7 +539,14 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     la.dx32 = h->tensor ? nullptr : h->dx32[L - 1];
     la.dx_hi = h->tensor ? h->dx_hi[L - 1] : nullptr; la.dx_lo = h->tensor ? h->dx_lo[L - 1] : nullptr;
     la.ldx = top.Np; la.alpha = h->alpha; la.colsum = h->colsum; la.trace = h->trace;
-    if (h->has_comm && la.ml) {
+    if (h->dp_push && la.ml) {
+        // partial sum|e|^beta exchanged over peer memory inside the loss kernel (no NCCL on the step)
+        ProfScope ps(h, KC_LOSS, s);
+        la.mode = 3; la.world = h->cfg.world_size; la.rank = h->cfg.rank;
+        la.step_counter = h->px_counters; la.error_flag = h->px_counters + 4;
+        for (int p = 0; p < la.world; p++) { la.asum_slot[p] = (float *)h->px_peer[2][p]; la.lflags[p] = (unsigned int *)h->px_peer[3][p] + DPX_FLAG_LOSS; }
+        launch_loss(la, s); (*launches)++;
+    } else if (h->has_comm && la.ml) {
         { ProfScope ps(h, KC_LOSS, s); la.mode = 1; launch_loss(la, s); }
         { ProfScope ps(h, KC_ALLREDUCE, s); GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, top.cur, ncclFloat, ncclSum, h->comm, s)); }
         { ProfScope ps(h, KC_LOSS, s); la.mode = 2; launch_loss(la, s); }
@@ -428,7 +560,8 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         const LayerInfo &ly = h->lay[l];
         if (h->tensor) {
             if (l != 1) { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
-            if (fused && h->persist) { /* all layers in one persistent launch after the backward chain */ }
+            if (h->dp_push && apply_update) { /* gradient tiles are pushed to their owners after the backward chain */ }
+            else if (fused && h->persist) { /* all layers in one persistent launch after the backward chain */ }
             else if (fused) { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_update(h->dwu[l], s)); (*launches)++; }
             else { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
         } else {
@@ -462,6 +595,13 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
             { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_update(ua, h->sm_count / 2, h->s_comm); (*launches)++; }
         }
+    }
+    if (h->dp_push && apply_update) {
+        // K1: every gradient tile -> its owner's receive slot; K2: owners reduce, update, broadcast the bf16 shadows
+        { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_dw_push(h->dpx_dev, h->sm_count, s)); (*launches)++; }
+        { ProfScope ps(h, KC_UPDATE, s); GGD_TRY(launch_reduce_update(h->dpx_dev, h->sm_count, h->px_k2_smem, s)); (*launches)++; }
+        GGD_CUDA(cudaGetLastError());
+        return GGD_OK;
     }
     if (fused && h->persist) {
         // weight gradients + updates of all layers, bias gradients + updates and the bunch counter: one launch
@@ -649,6 +789,11 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     h->stats.device_ms = ms;
     for (int b = 0; b < nb; b++) h->losses[b] = (float)tr[b];
     h->stats.d2h_bytes = nb * sizeof(double);
+    if (h->dp_push) {
+        unsigned int err = 0;
+        GGD_CUDA(cudaMemcpy(&err, h->px_counters + 4, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) { set_error("data-parallel step: rank %u did not arrive within the timeout (ranks must train the same number of bunches)", err - 1); return GGD_ENCCL; }
+    }
     if (h->dp_p2p) {
         unsigned int err = 0;
         GGD_CUDA(cudaMemcpy(&err, h->dp_counters + 2 * GGD_MAXLAYER, sizeof err, cudaMemcpyDeviceToHost));
@@ -766,9 +911,13 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         h->has_comm = true;
         const char *ov = getenv("GGD_DP_OVERLAP");
         h->dp_overlap = ov ? atoi(ov) : 0;
+        // GGD_DP_MODE: push (default when the bunch is one reduction tile) | pull (dp_update.cu) | nccl (allreduce)
+        const char *dm = getenv("GGD_DP_MODE");
         const char *pm = getenv("GGD_DP_P2P");
-        if (!(pm && atoi(pm) == 0) && world <= DP_MAX_RANKS && h->tensor) {   // (the fp32 validation path reads the master weights)
-            int rc = dp_p2p_setup(h);
+        const bool want_nccl = (dm && !strcmp(dm, "nccl")) || (pm && atoi(pm) == 0);
+        const bool want_pull = dm && !strcmp(dm, "pull");
+        if (!want_nccl && world <= DP_MAX_RANKS && h->tensor) {   // (the fp32 validation path reads the master weights)
+            int rc = (!want_pull && h->Mp == 128) ? dp_push_setup(h) : dp_p2p_setup(h);
             if (rc != GGD_OK) return fail(rc);
         }
     }
@@ -787,6 +936,11 @@ int ggd_destroy(ggd_handle *h)
     if (h->dp_p2p)
         for (int p = 0; p < h->cfg.world_size; p++)
             for (int k = 0; k < 5; k++) if (p != h->cfg.rank && h->peer_base[k][p]) cudaIpcCloseMemHandle(h->peer_base[k][p]);
+    if (h->dp_push)
+        for (int p = 0; p < h->cfg.world_size; p++)
+            for (int k = 0; k < 7; k++) if (p != h->cfg.rank && h->px_peer[k][p]) cudaIpcCloseMemHandle(h->px_peer[k][p]);
+    cudaFree(h->px_rbuf); cudaFree(h->px_bias); cudaFree(h->px_asum); cudaFree(h->px_flags); cudaFree(h->px_counters); cudaFree(h->dpx_dev);
+    cudaFree(h->px_peerP_dev); cudaFree(h->px_woff_dev);
     cudaFree(h->dp_flags); cudaFree(h->dp_counters);
     if (h->has_comm) ncclCommDestroy(h->comm);
     cudaFree(h->P); cudaFree(h->Dl); cudaFree(h->G); cudaFree(h->Phi); cudaFree(h->Plo);
@@ -958,6 +1112,13 @@ int ggd_get_weights(ggd_handle *h, float *const *weights, float *const *bias)
     GGD_CUDA(cudaSetDevice(h->cfg.gpu));
     GGD_CUDA(cudaStreamSynchronize(h->s_main));
     if (h->dp_p2p) GGD_TRY(dp_p2p_gather_master(h));
+    if (h->dp_push) {
+        // the fp32 master of a tile lives on its owner: pull the foreign tiles (between two cross-rank barriers)
+        GGD_TRY(dp_barrier(h));
+        launch_gather_master(h->dpx_dev, h->px_peerP_dev, h->px_woff_dev, h->sm_count * 2, h->s_main);
+        GGD_CUDA(cudaStreamSynchronize(h->s_main));
+        GGD_TRY(dp_barrier(h));
+    }
     for (int l = 1; l < h->L; l++) {
         const LayerInfo &ly = h->lay[l];
         GGD_CUDA(cudaMemcpy2D(weights[l], ly.cur * sizeof(float), h->P + ly.w_off, ly.Np * sizeof(float), ly.cur * sizeof(float), ly.prev, cudaMemcpyDeviceToHost));

@@ -8,6 +8,7 @@
 //   update_kernel       kernUpdatedelta + kernAccSum for weights AND biases in one launch
 //                       (DevFunc.cu:490-507, 427-443; BP_GPU.cu:433-437)
 #include "kernels.cuh"
+#include "pipe.cuh"
 #include <math.h>
 
 namespace ggd {
@@ -101,6 +102,34 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
             }
             __syncthreads();
             if (a.mode == 1) return;
+            if (a.mode == 3) {
+                // exchange the partial sums with every rank (warp 0 of this block owns the block's 32 columns)
+                if (ty == 0) {
+                    const unsigned int step = *a.step_counter + 1u;
+                    if (live)
+                        for (int p = 0; p < a.world; p++) a.asum_slot[p][(size_t)a.rank * a.D + d] = s_col[tx];
+                    __threadfence_system();
+                    __syncwarp();
+                    if (tx == 0)
+                        for (int p = 0; p < a.world; p++)
+                            if (p != a.rank) st_release_sys_u32(a.lflags[p] + a.rank * 16 + blockIdx.x, step);
+                    if (tx < a.world && tx != a.rank) {
+                        const unsigned int *f = a.lflags[a.rank] + tx * 16 + blockIdx.x;
+                        const long long t0 = clock64();
+                        while ((int)(ld_acquire_sys_u32(f) - step) < 0) {
+                            if (clock64() - t0 > (1ll << 32)) { *a.error_flag = 1u + tx; break; }
+                            __nanosleep(32);
+                        }
+                    }
+                    __syncwarp();
+                    if (live) {
+                        float t = 0.0f;
+                        for (int p = 0; p < a.world; p++) t += ld_relaxed_sys_f32(a.asum_slot[a.rank] + (size_t)p * a.D + d);   // rank order
+                        s_col[tx] = t;
+                    }
+                }
+                __syncthreads();
+            }
         } else {
             if (ty == 0) s_col[tx] = live ? a.colsum[d] : 0.0f;
             __syncthreads();

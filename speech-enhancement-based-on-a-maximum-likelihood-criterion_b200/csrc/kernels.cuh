@@ -35,7 +35,14 @@ struct LossArgs {
     float *alpha;       // [D] GGD scale factors (kept for CrossValid2)
     float *colsum;      // [D] sum_m |e|^beta  (partial in mode 1, global in mode 2)
     double *trace;      // per-bunch loss trace, indexed by ctl->bunch_idx (may be NULL)
-    int mode;           // 0 = fused single pass-pair, 1 = column sums only, 2 = gradient from `colsum`
+    int mode;           // 0 = fused single pass-pair, 1 = column sums only, 2 = gradient from `colsum`,
+                        // 3 = data-parallel in ONE kernel: partial column sums are stored into every rank's slot over
+                        //     NVLink peer memory, flagged, and summed in rank order (dp_push.cuh)
+    float *asum_slot[8];            // mode 3: every rank's receive area [world][D]
+    unsigned int *lflags[8];        // mode 3: every rank's loss flags [world][16] (one per source rank and block)
+    const unsigned int *step_counter;   // mode 3: completed data-parallel steps (flag value = *step_counter + 1)
+    unsigned int *error_flag;
+    int world, rank;
 };
 void launch_loss(const LossArgs &a, cudaStream_t s);
 

@@ -8,9 +8,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LS, MS, NB = [70, 96, 80, 33], 128, 6
+NAMED = [1799, 2048, 2048, 2048, 257]
 
 
-def _data(world):
+def _data(world, LS=LS, NB=NB):
     sys.path.insert(0, ROOT)
     from oracle import oracle as O
     rng = np.random.RandomState(13)
@@ -20,12 +21,12 @@ def _data(world):
     return W, b, x, t
 
 
-def _rank(rank, world, uid, ml, beta, precision, q):
+def _rank(rank, world, uid, ml, beta, precision, q, LS=LS, NB=NB):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import load_pkg
     pkg = load_pkg()
-    W, b, x, t = _data(world)
+    W, b, x, t = _data(world, LS, NB)
     net = pkg.BP_GPU(0, rank, len(LS), LS, MS, 0.1, 0.9, 1e-5, W, b, beta, ml, precision=precision, world_size=world, rank=rank,
                      nccl_unique_id=uid)
     net.train(NB * MS, x[rank], t[rank])
@@ -67,4 +68,38 @@ def test_two_gpu_dp_equals_unsharded(pkg, oracle, ml, beta, precision):
             assert np.allclose(r[4], lo, rtol=5e-3)
     # both ranks hold identical weights
     for a, c in zip(res[0][1], res[1][1]):
+        assert np.array_equal(a, c)
+
+
+def test_two_gpu_dp_named_shape(pkg, oracle):
+    """the named network, 128 frames per GPU (global minibatch 256): gradient tiles pushed to their owners over NVLink,
+    owner-side update, shadow broadcast -- against the oracle on the unsharded minibatch"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from se_ml_b200.bp_gpu import nccl_unique_id
+    world, nb = 2, 3
+    uid = nccl_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_rank, args=(r, world, uid, 1, 1.5, 0, q, NAMED, nb)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(60)
+    W, b, x, t = _data(world, NAMED, nb)
+    xg = np.concatenate([x[:, i * MS:(i + 1) * MS].reshape(world * MS, -1) for i in range(nb)])
+    tg = np.concatenate([t[:, i * MS:(i + 1) * MS].reshape(world * MS, -1) for i in range(nb)])
+    orc = oracle.OracleNet(NAMED, world * MS, 0.1, 0.9, 1e-5, 1.5, 1, W, b)
+    lo, al = orc.train(xg, tg)
+    Wo, bo = orc.weights()
+    for r in res:
+        for a, c, w0 in zip(r[1] + r[2], Wo + bo, W + b):
+            assert np.linalg.norm(a - c) <= 1e-3 * max(np.linalg.norm(c), 1e-6)
+            assert np.linalg.norm((a - w0) - (c - w0)) <= 2e-3 * max(np.linalg.norm(c - w0), 1e-6)   # the update itself
+        assert np.linalg.norm(r[3] - al[-1]) <= 1e-3 * np.linalg.norm(al[-1])
+        assert np.allclose(r[4], lo, rtol=5e-3)
+    for a, c in zip(res[0][1] + res[0][2], res[1][1] + res[1][2]):
         assert np.array_equal(a, c)
