@@ -28,6 +28,15 @@ __device__ __forceinline__ int owner_of(const DpxArgs *gp, int t)
     return o;
 }
 
+__device__ __forceinline__ void xstamp(const DpxArgs *gp, int kernel, int slot)
+{
+    if (gp->trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        gp->trace[((size_t)kernel * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+}
+
 // wait until flags[base + p] >= step for every peer p; bounded (a lost peer must not hang the GPU)
 __device__ bool wait_peers(const DpxArgs *gp, int base, unsigned int step)
 {
@@ -53,7 +62,8 @@ constexpr int B_PART = TK * BK * 2, B_STAGE = KB * 2 * B_PART;                  
 constexpr int ROWS = 16, QUARTERS = TK / ROWS;
 constexpr int STAGE = ROWS * TN * 4;        // 8 KB
 constexpr int STAGES = 8;
-constexpr int SMEM = A_SLOT + B_STAGE + STAGES * STAGE + 1024;
+constexpr int B_STAGES = 3;                 // y^T ring: the MMA chain must not wait for an L2 round trip per tile
+constexpr int SMEM = A_SLOT + B_STAGES * B_STAGE + STAGES * STAGE + 1024;
 constexpr int NTHREADS = 384;
 constexpr int TMEM_COLS = 2 * TK;
 }  // namespace k1
@@ -63,8 +73,8 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
     using namespace k1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *a_slot = smem, *b_stage = smem + A_SLOT, *ring = b_stage + B_STAGE;
-    __shared__ __align__(8) uint64_t a_full, a_empty, b_full, b_empty, t_full[2], t_empty[2], st_done[STAGES], st_empty[STAGES];
+    uint8_t *a_slot = smem, *b_ring = smem + A_SLOT, *ring = b_ring + B_STAGES * B_STAGE;
+    __shared__ __align__(8) uint64_t a_full, a_empty, b_full[B_STAGES], b_empty[B_STAGES], t_full[2], t_empty[2], st_done[STAGES], st_empty[STAGES];
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_last;
 
@@ -75,7 +85,8 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
 
     if (warp == 1) {
         if (lane == 0) {
-            mbar_init(&a_full, 1); mbar_init(&a_empty, 1); mbar_init(&b_full, 1); mbar_init(&b_empty, 1);
+            mbar_init(&a_full, 1); mbar_init(&a_empty, 1);
+            for (int s = 0; s < B_STAGES; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
             for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
             for (int s = 0; s < STAGES; s++) { mbar_init(&st_done[s], 8); mbar_init(&st_empty[s], 1); }
             fence_mbar_init();
@@ -87,7 +98,9 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x == 0) xstamp(gp, 0, 0);
     pdl_wait();
+    if (threadIdx.x == 0) xstamp(gp, 0, 1);
     const int bunch_row0 = gp->ctl->bunch_idx * gp->rows_per_bunch;
     const unsigned int step = gp->counters[0] + 1u;
 
@@ -111,13 +124,15 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
                             tma_load_2d(a_slot + kb * 2 * A_PART + A_PART + h * A_HALF, &L->a_lo, &a_full, tr.nt * TN + 64 * h, kb * BK);
                         }
                 }
-                mbar_wait_bounded(&b_empty, (it & 1) ^ 1, hang, 2, it);
-                mbar_expect_tx(&b_full, B_STAGE);
+                const int bs = it % B_STAGES;
+                mbar_wait_bounded(&b_empty[bs], ((it / B_STAGES) & 1) ^ 1, hang, 2, it);
+                mbar_expect_tx(&b_full[bs], B_STAGE);
+                uint8_t *b_stage = b_ring + bs * B_STAGE;
                 const int r0 = L->b_rows_from_ctl ? bunch_row0 : 0;
 #pragma unroll
                 for (int kb = 0; kb < KB; kb++) {
-                    tma_load_2d(b_stage + kb * 2 * B_PART, &L->b_hi, &b_full, tr.kt * TK, r0 + kb * BK);
-                    tma_load_2d(b_stage + kb * 2 * B_PART + B_PART, &L->b_lo, &b_full, tr.kt * TK, r0 + kb * BK);
+                    tma_load_2d(b_stage + kb * 2 * B_PART, &L->b_hi, &b_full[bs], tr.kt * TK, r0 + kb * BK);
+                    tma_load_2d(b_stage + kb * 2 * B_PART + B_PART, &L->b_lo, &b_full[bs], tr.kt * TK, r0 + kb * BK);
                 }
             }
         }
@@ -134,11 +149,12 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
                     mbar_wait_bounded(&a_full, a_cnt & 1, hang, 4, it);
                     a_cnt++;
                 }
-                mbar_wait_bounded(&b_full, it & 1, hang, 5, it);
+                const int bs = it % B_STAGES;
+                mbar_wait_bounded(&b_full[bs], (it / B_STAGES) & 1, hang, 5, it);
                 const int acc = it & 1;
                 mbar_wait_bounded(&t_empty[acc], ((it >> 1) & 1) ^ 1, hang, 6, it);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(a_slot), b0 = smem_u32(b_stage);
+                const uint32_t a0 = smem_u32(a_slot), b0 = smem_u32(b_ring + bs * B_STAGE);
                 const uint32_t d = tmem + acc * TK;
 #pragma unroll
                 for (int kb = 0; kb < KB; kb++) {
@@ -153,7 +169,7 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
                         umma_bf16(d, dah, dbh, idesc, 1);
                     }
                 }
-                umma_commit(&b_empty);
+                umma_commit(&b_empty[bs]);
                 umma_commit(&t_full[acc]);
                 XTile nx = tr;
                 if (t + 1 < t1) nx = decode_xtile(gp, t + 1);
@@ -181,7 +197,9 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
                     prev_ws = ws;
                 }
             }
+            xstamp(gp, 0, 2);
             tma_store_wait_all<0>();      // every gradient tile of this CTA has been written at its owner
+            xstamp(gp, 0, 3);
             asm volatile("fence.proxy.async;" ::: "memory");
         }
         __syncwarp();
@@ -261,6 +279,7 @@ __global__ void __launch_bounds__(k1::NTHREADS, 1) dw_push_kernel(const DpxArgs 
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
     // flag A: once EVERY CTA's stores (tiles and bias slots) are performed system-wide, tell all peers
     if (threadIdx.x == 0) {
+        xstamp(gp, 0, 4);
         __threadfence_system();
         const unsigned int prev = atomicAdd(gp->counters + 1, 1u);
         s_last = (prev == gridDim.x - 1);
@@ -314,10 +333,12 @@ __global__ void __launch_bounds__(k2::NTHREADS, 1) reduce_update_kernel(const Dp
         fence_mbar_init();
     }
     __syncthreads();
+    if (threadIdx.x == 0) xstamp(gp, 1, 0);
     pdl_wait();
+    if (threadIdx.x == 0) xstamp(gp, 1, 1);
     const unsigned int step = gp->counters[0] + 1u;
     // every peer's gradient tiles and bias partials of this step have landed in my receive slots
-    if (threadIdx.x == 0) s_ok = wait_peers(gp, DPX_FLAG_A, step) ? 1 : 0;
+    if (threadIdx.x == 0) { s_ok = wait_peers(gp, DPX_FLAG_A, step) ? 1 : 0; xstamp(gp, 1, 2); }
     __syncthreads();
     const bool ok = s_ok != 0;
 
@@ -368,7 +389,9 @@ __global__ void __launch_bounds__(k2::NTHREADS, 1) reduce_update_kernel(const Dp
                 }
                 prev_s = s;
             }
+            xstamp(gp, 1, 3);
             tma_store_wait_all<0>();      // my shadows are written in every rank's memory
+            xstamp(gp, 1, 4);
             asm volatile("fence.proxy.async;" ::: "memory");
         }
         __syncwarp();
@@ -440,7 +463,9 @@ __global__ void __launch_bounds__(k2::NTHREADS, 1) reduce_update_kernel(const Dp
             __threadfence_system();
             for (int p = 0; p < world; p++)
                 if (p != rank) st_release_sys_u32(gp->flags[p] + DPX_FLAG_B + rank, step);
+            xstamp(gp, 1, 5);
             wait_peers(gp, DPX_FLAG_B, step);
+            xstamp(gp, 1, 6);
             gp->counters[0] = step;
             gp->ctl->bunch_idx += 1;
             __threadfence();

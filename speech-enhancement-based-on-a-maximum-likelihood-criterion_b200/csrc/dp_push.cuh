@@ -46,6 +46,7 @@ struct DpxArgs {
     unsigned int *counters;          // local: {step, k1_done, k2_done}
     unsigned int *error_flag;        // local: 1 + rank that did not arrive in time
     unsigned int *hang;
+    unsigned long long *trace;       // optional (GGD_DPX_TRACE=1): [2 kernels][grid][8] globaltimer stamps of the last step
     StepCtl *ctl;
     int own_begin[DPX_MAX + 1];      // owner o holds tiles [own_begin[o], own_begin[o+1])
     int nlayers, total_tiles, world, rank, nbias, rows_per_bunch, M;

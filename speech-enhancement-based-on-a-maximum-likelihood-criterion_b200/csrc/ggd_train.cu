@@ -111,6 +111,7 @@ struct ggd_handle {
     void *px_peer[7][DPX_MAX];                    // IPC-mapped: rbuf, bias, asum, flags, Phi, Plo, P
     int px_own_begin[DPX_MAX + 1], px_slot_tiles, px_total_tiles, px_k2_smem, px_k2_stages, px_k2_stage_bytes;
     float **px_peerP_dev; long long *px_woff_dev;
+    unsigned long long *px_trace;
     // host mirrors / stats
     std::vector<float> losses;
     std::vector<float> h_out;
@@ -442,6 +443,7 @@ static int dp_push_setup(ggd_handle *h)
     GGD_CUDA(cudaMalloc(&h->px_counters, 8 * sizeof(unsigned int)));
     GGD_CUDA(cudaMemset(h->px_counters, 0, 8 * sizeof(unsigned int)));
     GGD_CUDA(cudaMalloc(&h->dpx_dev, sizeof(DpxArgs)));
+    { const char *ev = getenv("GGD_DPX_TRACE"); if (ev && atoi(ev) == 1) { GGD_CUDA(cudaMalloc(&h->px_trace, 2 * 160 * 8 * sizeof(unsigned long long))); GGD_CUDA(cudaMemset(h->px_trace, 0, 2 * 160 * 8 * sizeof(unsigned long long))); } }
     void *local[7] = {h->px_rbuf, h->px_bias, h->px_asum, h->px_flags, h->Phi, h->Plo, h->P};
     GGD_TRY(ipc_exchange(h, local, 7, h->px_peer));
     h->px_k2_smem = dp_push_k2_smem(world, &h->px_k2_stages, &h->px_k2_stage_bytes);
@@ -496,6 +498,7 @@ static int build_dpx(ggd_handle *h)
         a->flags[p] = (unsigned int *)h->px_peer[3][p];
     }
     a->counters = h->px_counters; a->error_flag = h->px_counters + 4; a->hang = h->hang_dev; a->ctl = h->ctl;
+    a->trace = h->px_trace;
     for (int o = 0; o <= world; o++) a->own_begin[o] = h->px_own_begin[o];
     a->total_tiles = h->px_total_tiles; a->world = world; a->rank = rank; a->nbias = (int)h->nbias;
     a->rows_per_bunch = h->M; a->M = h->M;
@@ -789,6 +792,25 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     h->stats.device_ms = ms;
     for (int b = 0; b < nb; b++) h->losses[b] = (float)tr[b];
     h->stats.d2h_bytes = nb * sizeof(double);
+    if (h->dp_push && h->px_trace) {
+        // per-CTA phase stamps of the LAST step's two exchange kernels (tuning aid, GGD_DPX_TRACE=1)
+        const int G = h->sm_count;
+        std::vector<unsigned long long> tr2((size_t)2 * G * 8);
+        GGD_CUDA(cudaMemcpy(tr2.data(), h->px_trace, tr2.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (int c = 0; c < G; c++) if (tr2[(size_t)c * 8]) t0 = std::min(t0, tr2[(size_t)c * 8]);
+        for (int k = 0; k < 2; k++) {
+            fprintf(stderr, "[rank %d] %s:", h->cfg.rank, k ? "K2 reduce_update" : "K1 dw_push");
+            for (int sl = 0; sl < 7; sl++) {
+                std::vector<double> v;
+                for (int c = 0; c < G; c++) { const unsigned long long x = tr2[((size_t)k * G + c) * 8 + sl]; if (x) v.push_back((double)(x - t0) * 1e-3); }
+                if (v.empty()) continue;
+                std::sort(v.begin(), v.end());
+                fprintf(stderr, " s%d[min %.1f med %.1f max %.1f]", sl, v.front(), v[v.size() / 2], v.back());
+            }
+            fprintf(stderr, " us\n");
+        }
+    }
     if (h->dp_push) {
         unsigned int err = 0;
         GGD_CUDA(cudaMemcpy(&err, h->px_counters + 4, sizeof err, cudaMemcpyDeviceToHost));
@@ -940,7 +962,7 @@ int ggd_destroy(ggd_handle *h)
         for (int p = 0; p < h->cfg.world_size; p++)
             for (int k = 0; k < 7; k++) if (p != h->cfg.rank && h->px_peer[k][p]) cudaIpcCloseMemHandle(h->px_peer[k][p]);
     cudaFree(h->px_rbuf); cudaFree(h->px_bias); cudaFree(h->px_asum); cudaFree(h->px_flags); cudaFree(h->px_counters); cudaFree(h->dpx_dev);
-    cudaFree(h->px_peerP_dev); cudaFree(h->px_woff_dev);
+    cudaFree(h->px_peerP_dev); cudaFree(h->px_woff_dev); cudaFree(h->px_trace);
     cudaFree(h->dp_flags); cudaFree(h->dp_counters);
     if (h->has_comm) ncclCommDestroy(h->comm);
     cudaFree(h->P); cudaFree(h->Dl); cudaFree(h->G); cudaFree(h->Phi); cudaFree(h->Plo);
