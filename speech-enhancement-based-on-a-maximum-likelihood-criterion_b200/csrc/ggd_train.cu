@@ -80,7 +80,9 @@ struct ggd_handle {
     bf16 *c_hi, *c_lo;
     size_t cap;         // frames
     std::map<const void *, size_t> pinned;
-    cudaStream_t s_main, s_comm;
+    cudaStream_t s_main, s_comm, s_copy;
+    std::vector<cudaEvent_t> ev_piece;   // upload pipeline: piece p of the chunk has landed
+    cudaEvent_t ev_c0, ev_c1;
     cudaEvent_t ev0, ev1, ev2;
     cudaEvent_t ev_dw[GGD_MAXLAYER], ev_bias, ev_done;   // fork/join between the compute and the communication stream
     size_t nbias;       // packed bias-gradient elements
@@ -721,6 +723,17 @@ static int set_ctl(ggd_handle *h, const float *d_in, const float *d_targ)
     return GGD_OK;
 }
 
+static int pin_host(ggd_handle *h, const float *src, size_t bytes)
+{
+    // pin the caller's (reused) buffer once so that the copy is a real DMA (the reference hands us pageable memory)
+    if ((h->cfg.flags & GGD_FLAG_PIN_HOST) && bytes >= (1u << 20) && h->pinned.find(src) == h->pinned.end()) {
+        cudaError_t e = cudaHostRegister(const_cast<float *>(src), bytes, cudaHostRegisterDefault);
+        if (e == cudaSuccess) h->pinned[src] = bytes;
+        else { cudaGetLastError(); h->pinned[src] = 0; }
+    }
+    return GGD_OK;
+}
+
 static int upload(ggd_handle *h, const float *src, float *dst, size_t bytes)
 {
     // pin the caller's (reused) buffer once so that the copy is a real DMA (the reference hands us pageable memory)
@@ -758,31 +771,58 @@ static int sync_main(ggd_handle *h)
     return GGD_ECUDA;
 }
 
-static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ)
+// Steps over one chunk.  With host_in/host_targ the chunk is uploaded in pieces of PIECE bunches on the copy stream
+// while the compute stream already trains on the pieces that have landed (H2D hidden behind the steps).
+static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ, const float *host_in = nullptr,
+                     const float *host_targ = nullptr)
 {
     const int nb = n_frames / h->M;   // trailing partial bunch dropped (BP_GPU.cu:173-180)
+    const int PIECE = 64;             // bunches per upload piece (a multiple of the 16-step graph)
+    const bool piped = host_in != nullptr;
+    const int D_ = h->units[h->L - 1];
     h->stats.steps = nb; h->stats.launches = 0;
     h->losses.assign(nb, 0.0f);
     if (nb == 0) { h->stats.device_ms = 0; return GGD_OK; }
     GGD_TRY(set_ctl(h, d_in, d_targ));
     GGD_CUDA(cudaMemsetAsync(h->trace, 0, h->trace_cap * sizeof(double), h->s_main));
     GGD_CUDA(cudaEventRecord(h->ev1, h->s_main));
-    if (h->tensor) { launch_split_rows(d_in, nb * h->M, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main); h->stats.launches++; }
-    if (h->cfg.flags & GGD_FLAG_NO_GRAPH) {
-        int launches = 0;
-        for (int b = 0; b < nb; b++) GGD_TRY(enqueue_step(h, h->s_main, true, &launches));
-        h->stats.launches += launches;
-    } else {
-        if (!h->g1) {
-            GGD_TRY(capture_graph(h, 1, &h->g1));
-            h->gN_steps = 16;
-            GGD_TRY(capture_graph(h, h->gN_steps, &h->gN));
-        }
-        int b = 0;
-        for (; b + h->gN_steps <= nb; b += h->gN_steps) GGD_CUDA(cudaGraphLaunch(h->gN, h->s_main));
-        for (; b < nb; b++) GGD_CUDA(cudaGraphLaunch(h->g1, h->s_main));
-        h->stats.launches += (long long)nb * h->launches_per_step;
+    const bool graphs = !(h->cfg.flags & GGD_FLAG_NO_GRAPH);
+    if (graphs && !h->g1) {
+        GGD_TRY(capture_graph(h, 1, &h->g1));
+        h->gN_steps = 16;
+        GGD_TRY(capture_graph(h, h->gN_steps, &h->gN));
     }
+    const int npieces = piped ? ceil_div(nb, PIECE) : 1;
+    if (piped) {
+        while ((int)h->ev_piece.size() < npieces) { cudaEvent_t e; GGD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_piece.push_back(e); }
+        // the copy stream starts after everything queued so far on the compute stream (the previous chunk is done: calls are blocking)
+        GGD_CUDA(cudaEventRecord(h->ev_c0, h->s_copy));
+        for (int p = 0; p < npieces; p++) {
+            const size_t f0 = (size_t)p * PIECE * h->M, f1 = (p == npieces - 1) ? (size_t)n_frames : (size_t)(p + 1) * PIECE * h->M;
+            GGD_CUDA(cudaMemcpyAsync(const_cast<float *>(d_in) + f0 * h->units[0], host_in + f0 * h->units[0], (f1 - f0) * h->units[0] * sizeof(float), cudaMemcpyHostToDevice, h->s_copy));
+            GGD_CUDA(cudaMemcpyAsync(const_cast<float *>(d_targ) + f0 * D_, host_targ + f0 * D_, (f1 - f0) * D_ * sizeof(float), cudaMemcpyHostToDevice, h->s_copy));
+            GGD_CUDA(cudaEventRecord(h->ev_piece[p], h->s_copy));
+        }
+        GGD_CUDA(cudaEventRecord(h->ev_c1, h->s_copy));
+    }
+    int launches = 0;
+    for (int p = 0; p < npieces; p++) {
+        const int b0 = piped ? p * PIECE : 0, b1 = piped ? std::min(nb, (p + 1) * PIECE) : nb;
+        if (piped) GGD_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_piece[p], 0));
+        if (h->tensor) {
+            launch_split_rows(d_in + (size_t)b0 * h->M * h->units[0], (b1 - b0) * h->M, h->units[0], h->c_hi + (size_t)b0 * h->M * h->upad[0],
+                              h->c_lo + (size_t)b0 * h->M * h->upad[0], h->upad[0], h->s_main);
+            h->stats.launches++;
+        }
+        if (!graphs) {
+            for (int b = b0; b < b1; b++) GGD_TRY(enqueue_step(h, h->s_main, true, &launches));
+        } else {
+            int b = b0;
+            for (; b + h->gN_steps <= b1; b += h->gN_steps) GGD_CUDA(cudaGraphLaunch(h->gN, h->s_main));
+            for (; b < b1; b++) GGD_CUDA(cudaGraphLaunch(h->g1, h->s_main));
+        }
+    }
+    h->stats.launches += graphs ? (long long)nb * h->launches_per_step : launches;
     GGD_CUDA(cudaEventRecord(h->ev2, h->s_main));
     std::vector<double> tr(nb);
     if (cudaMemcpyAsync(tr.data(), h->trace, nb * sizeof(double), cudaMemcpyDeviceToHost, h->s_main) != cudaSuccess) cudaGetLastError();
@@ -873,6 +913,8 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     auto fail = [&](int rc) { ggd_destroy(h); return rc; };
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s -> %s", #expr, cudaGetErrorString(_e)); return fail(_e == cudaErrorMemoryAllocation ? GGD_ENOMEM : GGD_ECUDA); } } while (0)
     CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev_c0)); CK(cudaEventCreate(&h->ev_c1));
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); CK(cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi)); }
     for (int l = 0; l < GGD_MAXLAYER; l++) CK(cudaEventCreateWithFlags(&h->ev_dw[l], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_bias, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
@@ -953,6 +995,10 @@ int ggd_destroy(ggd_handle *h)
     if (!h) return GGD_OK;
     cudaSetDevice(h->cfg.gpu);
     if (h->s_main) cudaStreamSynchronize(h->s_main);
+    if (h->s_copy) { cudaStreamSynchronize(h->s_copy); cudaStreamDestroy(h->s_copy); }
+    for (cudaEvent_t e : h->ev_piece) cudaEventDestroy(e);
+    if (h->ev_c0) cudaEventDestroy(h->ev_c0);
+    if (h->ev_c1) cudaEventDestroy(h->ev_c1);
     free_chunk(h);
     for (auto &kv : h->pinned) if (kv.second) cudaHostUnregister(const_cast<void *>(kv.first));
     if (h->dp_p2p)
@@ -1006,13 +1052,12 @@ int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ)
     GGD_TRY(ensure_chunk(h, n_frames));
     const int D = h->units[h->L - 1];
     const size_t bi = (size_t)n_frames * h->units[0] * sizeof(float), bt = (size_t)n_frames * D * sizeof(float);
-    GGD_CUDA(cudaEventRecord(h->ev0, h->s_main));
-    GGD_TRY(upload(h, in, h->c_in, bi));
-    GGD_TRY(upload(h, targ, h->c_targ, bt));
-    GGD_TRY(run_chunk(h, n_frames, h->c_in, h->c_targ));
+    GGD_TRY(pin_host(h, in, bi));
+    GGD_TRY(pin_host(h, targ, bt));
+    GGD_TRY(run_chunk(h, n_frames, h->c_in, h->c_targ, in, targ));
     float ms = 0;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    h->stats.h2d_ms = ms; h->stats.h2d_bytes = bi + bt;
+    if (n_frames / h->M > 0) cudaEventElapsedTime(&ms, h->ev_c0, h->ev_c1);
+    h->stats.h2d_ms = ms; h->stats.h2d_bytes = bi + bt;   // copy-stream time; it overlaps the steps of the earlier pieces
     return GGD_OK;
 }
 
