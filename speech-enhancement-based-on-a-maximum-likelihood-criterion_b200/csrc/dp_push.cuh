@@ -54,7 +54,7 @@ struct DpxArgs {
     float mom, lr, Mg;
 };
 
-constexpr int DPX_FLAG_A = 0, DPX_FLAG_B = DPX_MAX, DPX_FLAG_LOSS = 2 * DPX_MAX, DPX_FLAG_WORDS = 2 * DPX_MAX + 16 * DPX_MAX;
+constexpr int DPX_FLAG_A = 0, DPX_FLAG_B = DPX_MAX, DPX_FLAG_LOSS = 2 * DPX_MAX, DPX_FLAG_WORDS = 2 * DPX_MAX + LOSS_FLAGS_PER_RANK * DPX_MAX;
 
 int dp_push_init();
 int dp_push_k2_smem(int world, int *stages, int *stage_bytes);

@@ -8,6 +8,7 @@
 // [r*BN/S, (r+1)*BN/S)), summed in a fixed order, and only then the epilogue runs -- no partial sums
 // ever touch L2/HBM and the result is deterministic.
 #include "gemm_tc.cuh"
+#include "pipe.cuh"
 #include "../../include/ggd_train.h"
 #include <cudaTypedefs.h>
 
@@ -114,6 +115,130 @@ __device__ __forceinline__ void epilogue16(const GemmArgs &g, int i, int j, floa
     }
 }
 
+// |e|^p as in loss_kernel (kernels.cu): exact for beta = 2 and 1, otherwise exp2(p*log2 a)
+__device__ __forceinline__ float pow_abs_g(float a, float p)
+{
+    if (p == 2.0f) return a * a;
+    if (p == 1.0f) return a;
+    if (p == 0.0f) return 1.0f;
+    return (a > 0.0f) ? exp2f(p * __log2f(a)) : 0.0f;
+}
+
+// EPI_FWD_LOSS: the 128 epilogue threads hold rows (frames) i0..i0+127 and 16 columns [j, j+16) of the network output.
+// The tile (out = acc + bias, also stored as fp32) is staged in shared memory and the loss chain then runs COLUMN-parallel
+// in rolled loops (thread = one column x 16 rows): the epilogue is executed once per CTA, so straight-line unrolled code
+// (3 000 instructions in the first version) was bound by instruction fetch -- 11 us instead of 1.
+//   e = out - targ, s_d = sum over the 128 rows (8 row groups, fixed order), alpha_d = (beta*s_d/Mg)^(1/beta),
+//   dE/dx = (1/Mg) sgn(e)|e|^(beta-1) beta [/ alpha_d^beta] as bf16 hi/lo, exactly 0 at e == 0 (DevFunc.cu:388-391, 479-482).
+// With world > 1 the partial s_d are exchanged over peer memory (dp_push.cuh) so that alpha is the unsharded minibatch's.
+// `tg` / `bs`: targets and biases of this thread's row and 16 columns, loaded by the caller BEFORE it waits for the accumulator
+// (they do not depend on the GEMM; the epilogue warps are idle during the main loop anyway).
+__device__ __forceinline__ void epilogue_loss16(const GemmArgs &g, int i, int j, float *v, int t, const float *tg, const float *bs, int bunch)
+{
+    __shared__ float tile[128][17];
+    __shared__ float part[8][16], colscale[16];
+    const int row = i & 127;
+    const float beta = g.beta;
+    {
+        float4 *dst = reinterpret_cast<float4 *>(g.o32 + (size_t)i * g.ld32 + j);
+        const bool row_ok = i < g.I;
+#pragma unroll
+        for (int x = 0; x < 16; x++) {
+            const float o = (row_ok && j + x < g.D) ? v[x] + bs[x] : 0.0f;
+            v[x] = o;
+            tile[row][x] = o - tg[x];     // e (0 for rows / columns outside the net output: tg is 0 there)
+        }
+#pragma unroll
+        for (int x = 0; x < 4; x++) dst[x] = make_float4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+    }
+    if (t == 64) stamp(g, 10);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t == 64) stamp(g, 11);
+    const int col = t & 15, grp = t >> 4, d = j + col;
+    const int i0 = i - row;
+    const bool live = d < g.D;
+    {
+        float s = 0.0f;
+#pragma unroll
+        for (int m = 0; m < 16; m++) s += pow_abs_g(fabsf(tile[grp * 16 + m][col]), beta);
+        part[grp][col] = s;
+    }
+    if (t == 64) stamp(g, 12);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t < 16) {
+        float s = 0.0f;
+#pragma unroll 1
+        for (int q = 0; q < 8; q++) s += part[q][t];
+        if (g.world > 1 && g.ml) {
+            // frame-sharded data parallelism: alpha needs the sum over the GLOBAL minibatch
+            const unsigned int step = *g.step_counter + 1u;
+            const int chunk = j >> 4;
+            if (live)
+                for (int pr = 0; pr < g.world; pr++) g.asum_slot[pr][(size_t)g.rank * g.D + d] = s;
+            __threadfence_system();
+            __syncwarp(0x0000ffffu);
+            if (t == 0)
+                for (int pr = 0; pr < g.world; pr++)
+                    if (pr != g.rank) st_release_sys_u32(g.lflags[pr] + g.rank * LOSS_FLAGS_PER_RANK + chunk, step);
+            if (t < g.world && t != g.rank) {
+                const unsigned int *f = g.lflags[g.rank] + t * LOSS_FLAGS_PER_RANK + chunk;
+                const long long t0 = clock64();
+                while ((int)(ld_acquire_sys_u32(f) - step) < 0) {
+                    if (clock64() - t0 > (1ll << 32)) { *g.error_flag = 1u + t; break; }
+                    __nanosleep(32);
+                }
+            }
+            __syncwarp(0x0000ffffu);
+            if (live) {
+                s = 0.0f;
+                for (int pr = 0; pr < g.world; pr++) s += ld_relaxed_sys_f32(g.asum_slot[g.rank] + (size_t)pr * g.D + d);   // rank order
+            }
+        }
+        float pa = 1.0f, contrib = 0.0f;
+        if (live) {
+            if (g.ml) {
+                const float v1 = s / (float)g.Mg;
+                const float v2 = v1 * beta;
+                // (the 16 threads of this block are alone on their scheduler: hardware exp2/log2, rel. error ~1e-6)
+                const float al = (v2 > 0.0f) ? exp2f(__log2f(v2) / beta) : 0.0f;
+                g.alpha[d] = al;
+                pa = (beta == 2.0f) ? al * al : ((beta == 1.0f) ? al : v2);     // alpha^beta == beta*s/Mg by definition
+                contrib = 0.69314718056f * __log2f(al) + s / ((float)g.Mg * pa);     // ln alpha_d + sum_m (|e|/alpha_d)^beta / M
+            } else {
+                contrib = s / (float)g.Mg;                        // E_beta = sum |e|^beta / M
+            }
+        }
+        colscale[t] = (g.ml ? beta / pa : beta) / (float)g.Mg;
+        if (g.loss_trace) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) contrib += __shfl_xor_sync(0x0000ffffu, contrib, o);
+            if (t == 0) atomicAdd(g.loss_trace + bunch, (double)contrib);
+        }
+    }
+    if (t == 0) stamp(g, 13);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    {
+        const float scale = colscale[col];
+        bf16 *oh = g.o_hi + (size_t)i0 * g.ldo + d, *ol = g.o_lo + (size_t)i0 * g.ldo + d;
+#pragma unroll 8
+        for (int m = 0; m < 16; m++) {
+            const int r = grp * 16 + m;
+            const float ee = tile[r][col];
+            float rr = 0.0f;
+            if (ee != 0.0f) {
+                rr = pow_abs_g(fabsf(ee), beta - 1.0f) * scale;
+                rr = (ee > 0.0f) ? rr : -rr;
+            }
+            bf16 hv, lv;
+            split_bf16(rr, hv, lv);
+            oh[(size_t)r * g.ldo] = hv;
+            ol[(size_t)r * g.ldo] = lv;
+        }
+    }
+    if (t == 64) stamp(g, 14);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // tile / part / colscale are reused by the next 16-column chunk
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -150,6 +275,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    float loss_tg[16], loss_bs[16];   // EPI_FWD_LOSS: prefetched targets / biases (dead code otherwise)
+    int loss_bunch = 0;
     // everything above overlapped the tail of the previous kernel (PDL); from here on we read what it produced
     pdl_wait();
     const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
@@ -221,6 +348,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         __syncwarp();
     } else {
         // ===== epilogue warps: wait for the accumulator =====
+        if constexpr (EPI == EPI_FWD_LOSS) {
+            // targets and biases of this thread's row / first 16-column chunk: requested now, used after the main loop
+            const int qq = warp & 3, ii = i0 + qq * 32 + lane, jj = j0 + rank * (BN / S);
+            loss_bunch = g.ctl->bunch_idx;
+            const bool row_ok = ii < g.I;
+            const float *trow = g.ctl->targ + ((size_t)loss_bunch * g.I + (row_ok ? ii : 0)) * g.D + jj;
+#pragma unroll
+            for (int x = 0; x < 16; x++) {
+                loss_tg[x] = (row_ok && jj + x < g.D) ? __ldg(trow + x) : 0.0f;
+                loss_bs[x] = (jj + x < g.D) ? __ldg(g.bias + jj + x) : 0.0f;
+            }
+        }
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
         if (threadIdx.x == 64) stamp(g, 6);
@@ -267,7 +406,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     v[4 * e] += t.x; v[4 * e + 1] += t.y; v[4 * e + 2] += t.z; v[4 * e + 3] += t.w;
                 }
             }
-            epilogue16<EPI>(g, i0 + row, j0 + rank * W + c, v);
+            if constexpr (EPI == EPI_FWD_LOSS) {
+                if (c > 0) {   // further chunks of a wide tile (S < 4): load inline
+                    const int ii = i0 + row, jj = j0 + rank * W + c;
+                    const bool row_ok = ii < g.I;
+                    const float *trow = g.ctl->targ + ((size_t)loss_bunch * g.I + (row_ok ? ii : 0)) * g.D + jj;
+#pragma unroll
+                    for (int x = 0; x < 16; x++) {
+                        loss_tg[x] = (row_ok && jj + x < g.D) ? __ldg(trow + x) : 0.0f;
+                        loss_bs[x] = (jj + x < g.D) ? __ldg(g.bias + jj + x) : 0.0f;
+                    }
+                }
+                epilogue_loss16(g, i0 + row, j0 + rank * W + c, v, row, loss_tg, loss_bs, loss_bunch);
+            }
+            else epilogue16<EPI>(g, i0 + row, j0 + rank * W + c, v);
         }
     }
     if (threadIdx.x == 64) stamp(g, 8);
@@ -337,6 +489,7 @@ static int launch_bn(const GemmPlan &p, cudaStream_t s)
     switch (key) {
     case 10 + EPI_FWD_SIGMOID: return launch_inst<BN, false, true, EPI_FWD_SIGMOID>(p, s);
     case 10 + EPI_FWD_LINEAR:  return launch_inst<BN, false, true, EPI_FWD_LINEAR>(p, s);
+    case 10 + EPI_FWD_LOSS:    return launch_inst<BN, false, true, EPI_FWD_LOSS>(p, s);
     case 10 + EPI_STORE_F32:   return launch_inst<BN, false, true, EPI_STORE_F32>(p, s);
     case 0 + EPI_DX_DSIGMOID:  return launch_inst<BN, false, false, EPI_DX_DSIGMOID>(p, s);
     case 0 + EPI_STORE_F32:    return launch_inst<BN, false, false, EPI_STORE_F32>(p, s);
@@ -369,6 +522,7 @@ static int prep_bn()
     int rc;
     if ((rc = prep_inst<BN, false, true, EPI_FWD_SIGMOID>())) return rc;
     if ((rc = prep_inst<BN, false, true, EPI_FWD_LINEAR>())) return rc;
+    if ((rc = prep_inst<BN, false, true, EPI_FWD_LOSS>())) return rc;
     if ((rc = prep_inst<BN, false, true, EPI_STORE_F32>())) return rc;
     if ((rc = prep_inst<BN, false, false, EPI_DX_DSIGMOID>())) return rc;
     if ((rc = prep_inst<BN, false, false, EPI_STORE_F32>())) return rc;

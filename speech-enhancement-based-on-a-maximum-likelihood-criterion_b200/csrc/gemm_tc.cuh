@@ -20,8 +20,12 @@ enum GemmEpilogue {
     EPI_FWD_SIGMOID = 0,  // + bias, sigmoid, write bf16 hi/lo activations (kernMultiCopy + kernSigmoid fused)
     EPI_FWD_LINEAR = 1,   // + bias, write fp32 network output
     EPI_DX_DSIGMOID = 2,  // * y(1-y), write bf16 hi/lo dE/dx of the previous layer (kernDsigmoid fused)
-    EPI_STORE_F32 = 3     // plain fp32 store (weight gradient)
+    EPI_STORE_F32 = 3,    // plain fp32 store (weight gradient)
+    EPI_FWD_LOSS = 4      // output layer of a TRAINING step: + bias, fp32 network output AND the whole loss-gradient chain
+                          // (BP_GPU.cu:408-424) in the epilogue: e = out - targ, s_d = sum_m |e|^beta, alpha_d, dE/dx as bf16 hi/lo
 };
+
+constexpr int LOSS_FLAGS_PER_RANK = 32;   // data-parallel alpha exchange: one flag per source rank and 16-column chunk
 
 struct GemmArgs {
     const StepCtl *ctl;
@@ -37,6 +41,18 @@ struct GemmArgs {
     const bf16 *y_hi, *y_lo;  // EPI_DX_DSIGMOID: activations of the layer whose dE/dx is produced, pitch ldy
     int ldy;
     unsigned long long *trace;   // optional [ctas][16] globaltimer stamps of the pipeline phases (ggd_debug_gemm_timed)
+    // ---- EPI_FWD_LOSS only
+    int D;                 // real output units (== J)
+    int Mg;                // frames of the GLOBAL minibatch
+    float beta;            // shapefactor
+    int ml;                // MLflag == 1
+    float *alpha;          // [D]
+    double *loss_trace;    // per-bunch loss, indexed by ctl->bunch_idx (may be NULL)
+    int world, rank;       // world > 1: partial column sums are exchanged over peer memory (dp_push.cuh)
+    float *asum_slot[8];   // every rank's receive area [world][D]
+    unsigned int *lflags[8];   // every rank's flags [world][LOSS_FLAGS_PER_RANK]
+    const unsigned int *step_counter;
+    unsigned int *error_flag;
 };
 
 struct GemmPlan {

@@ -88,6 +88,8 @@ struct ggd_handle {
     size_t nbias;       // packed bias-gradient elements
     // plans + graphs
     GemmPlan fwd[GGD_MAXLAYER], dxp[GGD_MAXLAYER], dwp[GGD_MAXLAYER];
+    GemmPlan fwd_loss;  // output layer of a training step: the loss-gradient chain runs in its epilogue (EPI_FWD_LOSS)
+    bool fuse_loss;
     DwUpdPlan dwu[GGD_MAXLAYER];
     bool fused;         // gradient GEMM + update fused (single GPU, tensor path)
     bool persist;       // fused AND the bunch is one reduction tile: one persistent launch for all layers (dw_persist.cu)
@@ -253,6 +255,21 @@ static int build_plans(ggd_handle *h)
             a.W = h->P + ly.w_off; a.D = h->Dl + ly.w_off;
             a.w_hi = h->Phi + ly.w_off; a.w_lo = h->Plo + ly.w_off;
             a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg; a.wc = h->cfg.weightcost;
+        }
+    }
+    if (h->fuse_loss) {
+        const LayerInfo &top = h->lay[L - 1];
+        GemmPlan &p = h->fwd_loss;
+        p = h->fwd[L - 1];
+        p.epi = EPI_FWD_LOSS;
+        GemmArgs &a = p.args;
+        a.o_hi = h->dx_hi[L - 1]; a.o_lo = h->dx_lo[L - 1]; a.ldo = top.Np;
+        a.D = top.cur; a.Mg = h->Mg; a.beta = h->cfg.shapefactor; a.ml = (h->cfg.MLflag == 1);
+        a.alpha = h->alpha; a.loss_trace = h->trace;
+        a.world = h->dp_push ? h->cfg.world_size : 1; a.rank = h->cfg.rank;
+        if (h->dp_push) {
+            a.step_counter = h->px_counters; a.error_flag = h->px_counters + 4;
+            for (int q = 0; q < a.world; q++) { a.asum_slot[q] = (float *)h->px_peer[2][q]; a.lflags[q] = (unsigned int *)h->px_peer[3][q] + DPX_FLAG_LOSS; }
         }
     }
     if (h->persist) {
@@ -513,11 +530,14 @@ static int build_dpx(ggd_handle *h)
 }
 
 // ---- one training step (forward, loss gradient, backward, update); stream-ordered, no host sync ----
-static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches)
+static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches, bool train = false)
 {
     const int L = h->L;
     if (h->tensor) {
-        for (int l = 1; l < L; l++) { ProfScope ps(h, KC_FWD, s); GGD_TRY(launch_gemm_tc(h->fwd[l], s)); (*launches)++; }
+        for (int l = 1; l < L; l++) {
+            ProfScope ps(h, KC_FWD, s);
+            GGD_TRY(launch_gemm_tc((train && h->fuse_loss && l == L - 1) ? h->fwd_loss : h->fwd[l], s)); (*launches)++;
+        }
     } else {
         launch_simt_gather_in(h->ctl, h->M, h->units[0], h->y32[0], h->upad[0], s); (*launches)++;
         for (int l = 1; l < L; l++) {
@@ -535,8 +555,8 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     const bool fused = h->fused && allow_fused && apply_update;
     const int L = h->L;
     const LayerInfo &top = h->lay[L - 1];
-    GGD_TRY(enqueue_forward(h, s, launches));
-    // ---- fused loss gradient (BP_GPU.cu:408-424)
+    GGD_TRY(enqueue_forward(h, s, launches, true));
+    // ---- fused loss gradient (BP_GPU.cu:408-424); with fuse_loss it already ran in the output layer's epilogue
     LossArgs la;
     memset(&la, 0, sizeof la);
     la.ctl = h->ctl; la.out = h->out32; la.ldo = top.Np; la.M = h->M; la.Mg = h->Mg; la.D = top.cur;
@@ -544,7 +564,8 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     la.dx32 = h->tensor ? nullptr : h->dx32[L - 1];
     la.dx_hi = h->tensor ? h->dx_hi[L - 1] : nullptr; la.dx_lo = h->tensor ? h->dx_lo[L - 1] : nullptr;
     la.ldx = top.Np; la.alpha = h->alpha; la.colsum = h->colsum; la.trace = h->trace;
-    if (h->dp_push && la.ml) {
+    if (h->fuse_loss) {
+    } else if (h->dp_push && la.ml) {
         // partial sum|e|^beta exchanged over peer memory inside the loss kernel (no NCCL on the step)
         ProfScope ps(h, KC_LOSS, s);
         la.mode = 3; la.world = h->cfg.world_size; la.rank = h->cfg.rank;
@@ -985,6 +1006,10 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
             if (rc != GGD_OK) return fail(rc);
         }
     }
+    {
+        const char *ev = getenv("GGD_FUSE_LOSS");   // 0: separate loss kernel (A-B / tuning)
+        h->fuse_loss = h->tensor && h->Mp == 128 && (world == 1 || h->dp_push) && !(ev && atoi(ev) == 0);
+    }
 #undef CK
     *out = h;
     return GGD_OK;
@@ -1328,9 +1353,13 @@ int ggd_debug_trace_step(ggd_handle *h, const float *in, const float *targ, int 
     const int D = h->units[h->L - 1], L = h->L;
     struct Item { int kind; int ctas; unsigned long long **slot; };
     std::vector<Item> items;
-    for (int l = 1; l < L; l++) items.push_back({0, h->fwd[l].splits * h->fwd[l].tiles_i * h->fwd[l].tiles_j, &h->fwd[l].args.trace});
+    for (int l = 1; l < L; l++) {
+        GemmPlan &fp = (h->fuse_loss && l == L - 1) ? h->fwd_loss : h->fwd[l];
+        items.push_back({0, fp.splits * fp.tiles_i * fp.tiles_j, &fp.args.trace});
+    }
     for (int l = L - 1; l > 0; l--) {
         if (l != 1) items.push_back({2, h->dxp[l].splits * h->dxp[l].tiles_i * h->dxp[l].tiles_j, &h->dxp[l].args.trace});
+        if (fused && h->fused && h->persist) continue;     // the persistent gradient+update kernel carries no stamps
         if (fused && h->fused) items.push_back({9, h->dwu[l].tiles_i * h->dwu[l].tiles_j, &h->dwu[l].args.trace});
         else items.push_back({3, h->dwp[l].tiles_i * h->dwp[l].tiles_j, &h->dwp[l].args.trace});
     }
@@ -1362,7 +1391,8 @@ int ggd_debug_trace_step(ggd_handle *h, const float *in, const float *targ, int 
         if (n >= max_launches) break;
         float *o = out + (size_t)n * 12;
         unsigned long long first = ~0ull, last = 0;
-        const int slots[8] = {1, 2, 3, 4, 6, 7, 8, 9};
+        int slots[8] = {1, 2, 3, 4, 6, 7, 8, 9};
+        if (getenv("GGD_TRACE_LOSS")) { const int alt[8] = {7, 10, 11, 12, 13, 14, 8, 9}; for (int k = 0; k < 8; k++) slots[k] = alt[k]; }
         std::vector<double> med[8];
         for (int c = 0; c < it.ctas; c++) {
             const unsigned long long *t = &hb[off + (size_t)c * 16];
