@@ -164,3 +164,27 @@ def test_named_shape_chunk_persistent(pkg, oracle):
         # the UPDATE itself must agree, not only the (barely moved) weights
         assert rel_err(Wg[l] - W[l], Wo[l] - W[l]) < 2e-3, l
         assert rel_err(bg[l] - b[l], bo[l] - b[l]) < 2e-3, l
+
+
+@pytest.mark.parametrize("M,MLflag,beta", [(50, 1, 1.5), (100, 0, 2.0), (128, 1, 1.0)])
+def test_chunk_ragged_bunch_production_path(pkg, oracle, M, MLflag, beta):
+    """ggd_train with bunches below the 128-frame tile (rows >= bunch are padding) and ragged layer widths: the fused
+    loss epilogue and the persistent gradient+update kernel must ignore the padding exactly"""
+    O = oracle
+    layersizes, nb = [7 * 33, 200, 130, 33], 7
+    W, b, x, t = make_case(O, layersizes, M * nb + 11, 31)
+    orc = O.OracleNet(layersizes, M, 0.1, 0.9, 1e-5, beta, MLflag, W, b)
+    lo, al = orc.train(x, t)
+    net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, 0.1, 0.9, 1e-5, W, b, beta, MLflag)
+    net.train(x.shape[0], x, t)
+    lg = net.losses()
+    assert len(lg) == nb
+    assert np.max(np.abs(lg - lo) / np.abs(lo)) < 5e-3
+    if MLflag == 1:
+        assert rel_err(net.alpha(), al[-1]) < 1e-3
+    Wg, bg = net.returnWeights()
+    Wo, bo = orc.weights()
+    for l in range(len(layersizes) - 1):
+        assert rel_err(Wg[l], Wo[l]) < 1e-3
+        assert rel_err(bg[l], bo[l]) < 1e-3
+        assert rel_err(Wg[l] - W[l], Wo[l] - W[l]) < 2e-3, l
