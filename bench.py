@@ -46,6 +46,28 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
 
 
+def gemm_probe(pkg, peaks):
+    """forward-layer GEMM (K = N = 2048) of gemm_tc.cu at 128 / 1024 / 4096 frames, warm, CUDA events inside the library"""
+    import ctypes as C
+    L = pkg.load_library()
+    PF = C.POINTER(C.c_float)
+    L.ggd_debug_gemm_timed.argtypes = [C.c_int] * 7 + [PF, PF, PF, C.c_int, PF, C.POINTER(C.c_ulonglong), C.c_int]
+    out = {}
+    rng = np.random.RandomState(0)
+    for M, bn, splits in ((128, 64, 4), (1024, 128, 1), (4096, 128, 1)):
+        A = rng.randn(M, 2048).astype(np.float32); B = rng.randn(2048, 2048).astype(np.float32)
+        D = np.zeros((M, 2048), np.float32)
+        ms = C.c_float()
+        rc = L.ggd_debug_gemm_timed(0, 1, M, 2048, 2048, bn, splits, A.ctypes.data_as(PF), B.ctypes.data_as(PF), D.ctypes.data_as(PF),
+                                    20, C.byref(ms), None, 0)
+        if rc != 0:
+            raise RuntimeError(L.ggd_last_error().decode())
+        alg = 2.0 * M * 2048 * 2048 / (ms.value * 1e-3) / 1e12
+        out["fwd_%dx2048x2048" % M] = {"us": ms.value * 1e3, "tflops_algorithmic": alg, "tflops_executed_bf16x3": 3 * alg,
+                                        "frac_of_bf16_sustained_executed": 3 * alg / peaks["bf16_sus"]}
+    return out
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -364,6 +386,16 @@ def main():
         except Exception as ex:     # the baseline is optional; never let it break the measurement
             ref_cuda = {"unavailable": str(ex)[:200]}
 
+    # ---- tensor-pipe evidence: the same tcgen05 GEMM kernel on the forward shape at bunch sizes where it is not
+    #      latency-bound (the 128-frame step cannot leave the HBM floor); algorithmic and executed
+    #      (bf16x3 = 3 MMAs per product) TFLOP/s against the measured bf16 peak
+    probe = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            probe = gemm_probe(pkg, peaks)
+        except Exception as ex:
+            probe = {"unavailable": str(ex)[:200]}
+
     # ---- LPS front end (second half of the metric): frames/s of the extraction kernel on synthetic 16 kHz noise
     lps = None
     if rank == 0 and not args.no_lps:
@@ -378,7 +410,7 @@ def main():
                            "global_minibatch": bunch * world, "l2": "inputs (737 MB/chunk) and weight state (250 MB) exceed the 126 MB L2",
                            "parallelism": "dp%d (frame-sharded; allreduce of sum|e|^beta and of the gradients)" % world},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "kernels": kern, "flops_per_frame": fpf, "reference_cuda": ref_cuda, "lps": lps,
+                "kernels": kern, "gemm_tensor_probe": probe, "flops_per_frame": fpf, "reference_cuda": ref_cuda, "lps": lps,
                 "tensor_frac_whole_step": (fpf * bunch * K / (ms * 1e-3) / 1e12) / peaks["bf16_sus"]}
         print(json.dumps(line), flush=True)
     net.close()

@@ -88,6 +88,25 @@ int ggd_reserve(ggd_handle *h, int n_frames);
 /* One call = one chunk: H2D copy, then one training step per full bunch; a trailing partial bunch is
  * dropped (BP_GPU.cu:173-180).  Blocking, like the reference. */
 int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ);
+/* Device-side loader: replaces the ARITHMETIC of Interface::Readchunk (Interface.cc:735-838).  The caller
+ * hands over the raw pfile records of one chunk exactly as they lie in the files (big-endian 32-bit words, 2 + dim per
+ * frame: sentence id, frame id, features) and, for every net-input row (already in the shuffled order of :750-754), the
+ * index of its first context frame inside the chunk.  Byte swap, z-score with mean / reciprocal std (noisy statistics on
+ * BOTH streams, indexed j % fea_dim for the targets), context expansion, target-frame selection and the operand split
+ * run on the GPU: 2 KB per frame cross PCIe instead of 8.2 KB per sample, and the host does no per-element work.
+ * Then trains like ggd_train (trailing partial bunch dropped).  Results are bit-identical to ggd_train on the host-expanded
+ * arrays. */
+typedef struct ggd_raw_chunk {
+    const unsigned int *fea_records;     /* n_frames * (2 + fea_dim) words, noisy-speech pfile */
+    const unsigned int *targ_records;    /* n_frames * (2 + layersizes[last]) words, clean-speech pfile */
+    int n_frames;                        /* raw frames in the chunk ("need", Interface.cc:729-733) */
+    int n_samples;                       /* net-input rows */
+    const int *sample_first_frame;       /* [n_samples], 0 <= f and f + fea_context <= n_frames */
+    int fea_dim, fea_context, targ_offset;
+    const float *mean, *dvar;            /* [fea_dim] */
+} ggd_raw_chunk;
+int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *chunk);
+
 /* Same, for a chunk that is already resident in device memory (fp32, same layouts). */
 int ggd_train_device(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ);
 

@@ -419,3 +419,41 @@ class PfileLoader:
             cur_sent += 1
             processed += n
         return ind, tg
+
+    def read_chunk_raw(self, starts, total, sent_en, idx, shuffle=True):
+        """The inputs of the device-side loader (ggd_train_raw) for the same chunk: raw big-endian records of the chunk's
+        frames and, per (shuffled) net-input row, the first context frame inside the chunk.  Consumes the SAME random
+        numbers as read_chunk, so a loader created with the same seed yields the same row order."""
+        last = idx == len(starts) - 1
+        if last:
+            need = int(self.sent_end[sent_en]) - starts[idx]
+            samples = total - self.cache * idx
+        else:
+            samples = self.cache
+            need = starts[idx + 1] - starts[idx]
+        order = list(range(samples))
+        if shuffle:
+            rand_index(order, self.rng)
+        f0 = starts[idx]
+        first = np.zeros(samples, np.int32)
+        cur_sent = int(np.searchsorted(self.sent_end, f0, side="right"))
+        processed, cur_frame_id, cur_sample = 0, f0, 0
+        while processed != need:
+            if self.sent_end[cur_sent] > need + f0:
+                n = need - processed
+            else:
+                n = int(self.sent_end[cur_sent]) - cur_frame_id
+            for j in range(0, n - self.ctx + 1):
+                if cur_sample >= samples:
+                    break
+                first[order[cur_sample]] = processed + j
+                cur_sample += 1
+            cur_frame_id = int(self.sent_end[cur_sent])
+            cur_sent += 1
+            processed += n
+
+        def records(x):
+            rec = np.zeros((need, 2 + x.shape[1]), ">u4")
+            rec[:, 2:] = x[f0:f0 + need].astype(">f4").view(">u4")
+            return rec.view(np.uint32)          # the bytes as they lie in the pfile, read as native words
+        return records(self.feats), records(self.targs), first

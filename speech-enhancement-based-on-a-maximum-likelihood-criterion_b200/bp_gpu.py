@@ -55,6 +55,7 @@ def load_library():
         L.ggd_destroy.argtypes = [C.c_void_p]
         L.ggd_train.argtypes = [C.c_void_p, C.c_int, PF, PF]
         L.ggd_reserve.argtypes = [C.c_void_p, C.c_int]
+        L.ggd_train_raw.argtypes = [C.c_void_p, C.c_void_p]
         L.ggd_train_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         for f in ("ggd_cv_sqerr", "ggd_cv_abserr", "ggd_cv_loglik"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int, PF, PF, PF]
@@ -81,6 +82,13 @@ def _f32(a):
     if a.dtype != np.float32 or not a.flags.c_contiguous:
         a = np.ascontiguousarray(a, dtype=np.float32)
     return a
+
+
+class RawChunk(C.Structure):
+    """ggd_raw_chunk (include/ggd_train.h)"""
+    _fields_ = [("fea_records", C.POINTER(C.c_uint)), ("targ_records", C.POINTER(C.c_uint)), ("n_frames", C.c_int), ("n_samples", C.c_int),
+                ("sample_first_frame", C.POINTER(C.c_int)), ("fea_dim", C.c_int), ("fea_context", C.c_int), ("targ_offset", C.c_int),
+                ("mean", C.POINTER(C.c_float)), ("dvar", C.POINTER(C.c_float))]
 
 
 class BP_GPU:
@@ -142,6 +150,22 @@ class BP_GPU:
     def train(self, n_frames, in_, targ):
         in_, targ = _f32(in_), _f32(targ)
         self._ck(self.L.ggd_train(self.h, n_frames, _fp(in_), _fp(targ)))
+
+    def train_raw(self, fea_records, targ_records, sample_first_frame, fea_dim, fea_context, targ_offset, mean, dvar):
+        """Device-side loader (ggd_train_raw): raw big-endian pfile records (uint32 [frames][2+dim]) + the first context
+        frame of every (shuffled) net-input row; byte swap, z-score, context expansion and target selection run on the GPU
+        (the arithmetic of Interface::Readchunk, Interface.cc:735-838)."""
+        fr = np.ascontiguousarray(fea_records, dtype=np.uint32)
+        tr = np.ascontiguousarray(targ_records, dtype=np.uint32)
+        first = np.ascontiguousarray(sample_first_frame, dtype=np.int32)
+        mean, dvar = _f32(mean), _f32(dvar)
+        c = RawChunk()
+        c.fea_records = fr.ctypes.data_as(C.POINTER(C.c_uint)); c.targ_records = tr.ctypes.data_as(C.POINTER(C.c_uint))
+        c.n_frames = fr.shape[0]; c.n_samples = first.size
+        c.sample_first_frame = first.ctypes.data_as(C.POINTER(C.c_int))
+        c.fea_dim, c.fea_context, c.targ_offset = fea_dim, fea_context, targ_offset
+        c.mean, c.dvar = _fp(mean), _fp(dvar)
+        self._ck(self.L.ggd_train_raw(self.h, C.byref(c)))
 
     def _cv(self, fn, n_frames, in_, targ):
         in_, targ = _f32(in_), _f32(targ)

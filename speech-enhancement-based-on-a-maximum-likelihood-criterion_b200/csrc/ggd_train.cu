@@ -75,6 +75,8 @@ struct ggd_handle {
     double *trace;
     size_t trace_cap;
     StepCtl *ctl;
+    // raw-record staging of the device-side loader (grow-only)
+    unsigned int *r_fea, *r_targ; int *r_first; float *r_norm; size_t r_cap_fea, r_cap_targ, r_cap_first, r_cap_norm;
     // chunk staging
     float *c_in, *c_targ, *c_out;
     bf16 *c_hi, *c_lo;
@@ -795,7 +797,7 @@ static int sync_main(ggd_handle *h)
 // Steps over one chunk.  With host_in/host_targ the chunk is uploaded in pieces of PIECE bunches on the copy stream
 // while the compute stream already trains on the pieces that have landed (H2D hidden behind the steps).
 static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ, const float *host_in = nullptr,
-                     const float *host_targ = nullptr)
+                     const float *host_targ = nullptr, bool presplit = false)
 {
     const int nb = n_frames / h->M;   // trailing partial bunch dropped (BP_GPU.cu:173-180)
     const int PIECE = 64;             // bunches per upload piece (a multiple of the 16-step graph)
@@ -830,7 +832,7 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     for (int p = 0; p < npieces; p++) {
         const int b0 = piped ? p * PIECE : 0, b1 = piped ? std::min(nb, (p + 1) * PIECE) : nb;
         if (piped) GGD_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_piece[p], 0));
-        if (h->tensor) {
+        if (h->tensor && !presplit) {
             launch_split_rows(d_in + (size_t)b0 * h->M * h->units[0], (b1 - b0) * h->M, h->units[0], h->c_hi + (size_t)b0 * h->M * h->upad[0],
                               h->c_lo + (size_t)b0 * h->M * h->upad[0], h->upad[0], h->s_main);
             h->stats.launches++;
@@ -882,6 +884,16 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
         GGD_CUDA(cudaMemcpy(&err, h->dp_counters + 2 * GGD_MAXLAYER, sizeof err, cudaMemcpyDeviceToHost));
         if (err) { set_error("data-parallel step: rank %u did not arrive within the timeout (ranks must train the same number of bunches)", err - 1); return GGD_ENCCL; }
     }
+    return GGD_OK;
+}
+
+template <typename T>
+static int grow(T **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return GGD_OK;
+    cudaFree(*buf); *buf = nullptr; *cap = 0;
+    GGD_CUDA(cudaMalloc(buf, need * sizeof(T)));
+    *cap = need;
     return GGD_OK;
 }
 
@@ -1034,6 +1046,7 @@ int ggd_destroy(ggd_handle *h)
             for (int k = 0; k < 7; k++) if (p != h->cfg.rank && h->px_peer[k][p]) cudaIpcCloseMemHandle(h->px_peer[k][p]);
     cudaFree(h->px_rbuf); cudaFree(h->px_bias); cudaFree(h->px_asum); cudaFree(h->px_flags); cudaFree(h->px_counters); cudaFree(h->dpx_dev);
     cudaFree(h->px_peerP_dev); cudaFree(h->px_woff_dev); cudaFree(h->px_trace);
+    cudaFree(h->r_fea); cudaFree(h->r_targ); cudaFree(h->r_first); cudaFree(h->r_norm);
     cudaFree(h->dp_flags); cudaFree(h->dp_counters);
     if (h->has_comm) ncclCommDestroy(h->comm);
     cudaFree(h->P); cudaFree(h->Dl); cudaFree(h->G); cudaFree(h->Phi); cudaFree(h->Plo);
@@ -1083,6 +1096,54 @@ int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ)
     float ms = 0;
     if (n_frames / h->M > 0) cudaEventElapsedTime(&ms, h->ev_c0, h->ev_c1);
     h->stats.h2d_ms = ms; h->stats.h2d_bytes = bi + bt;   // copy-stream time; it overlaps the steps of the earlier pieces
+    return GGD_OK;
+}
+
+int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *c)
+{
+    if (!h || !c || !c->fea_records || !c->targ_records || !c->sample_first_frame || !c->mean || !c->dvar || c->n_samples < 0 || c->n_frames < 0) {
+        set_error("ggd_train_raw: bad argument"); return GGD_EINVAL;
+    }
+    const int D = h->units[h->L - 1];
+    if (c->fea_dim < 1 || c->fea_context < 1 || c->fea_dim * c->fea_context != h->units[0]) {
+        set_error("ggd_train_raw: fea_dim %d x fea_context %d does not match layersizes[0] %d", c->fea_dim, c->fea_context, h->units[0]); return GGD_EINVAL;
+    }
+    if (c->targ_offset < 0 || c->targ_offset >= c->fea_context) { set_error("ggd_train_raw: targ_offset %d outside the context window", c->targ_offset); return GGD_EINVAL; }
+    if (c->n_samples > GGD_MAXCACHEFRAME) { set_error("n_samples %d exceeds MAXCACHEFRAME %d", c->n_samples, GGD_MAXCACHEFRAME); return GGD_EINVAL; }
+    for (int i = 0; i < c->n_samples; i++)
+        if (c->sample_first_frame[i] < 0 || c->sample_first_frame[i] + c->fea_context > c->n_frames) {
+            set_error("ggd_train_raw: sample %d starts at frame %d, outside the %d frames of the chunk", i, c->sample_first_frame[i], c->n_frames); return GGD_EINVAL;
+        }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, c->n_samples));
+    const size_t nf = (size_t)c->n_frames * (2 + c->fea_dim), nt = (size_t)c->n_frames * (2 + D);
+    GGD_TRY(grow(&h->r_fea, &h->r_cap_fea, nf));
+    GGD_TRY(grow(&h->r_targ, &h->r_cap_targ, nt));
+    GGD_TRY(grow(&h->r_first, &h->r_cap_first, (size_t)c->n_samples));
+    GGD_TRY(grow(&h->r_norm, &h->r_cap_norm, (size_t)2 * c->fea_dim));
+    GGD_TRY(pin_host(h, reinterpret_cast<const float *>(c->fea_records), nf * 4));
+    GGD_TRY(pin_host(h, reinterpret_cast<const float *>(c->targ_records), nt * 4));
+    GGD_CUDA(cudaEventRecord(h->ev_c0, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->r_fea, c->fea_records, nf * 4, cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->r_targ, c->targ_records, nt * 4, cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->r_first, c->sample_first_frame, (size_t)c->n_samples * sizeof(int), cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->r_norm, c->mean, (size_t)c->fea_dim * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->r_norm + c->fea_dim, c->dvar, (size_t)c->fea_dim * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaEventRecord(h->ev_c1, h->s_main));
+    ExpandArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.fea_rec = h->r_fea; ea.targ_rec = h->r_targ; ea.first = h->r_first; ea.mean = h->r_norm; ea.dvar = h->r_norm + c->fea_dim;
+    ea.samples = c->n_samples; ea.fea_dim = c->fea_dim; ea.ctx = c->fea_context; ea.targ_offset = c->targ_offset; ea.D = D;
+    ea.in32 = h->tensor ? nullptr : h->c_in;
+    ea.in_hi = h->tensor ? h->c_hi : nullptr; ea.in_lo = h->tensor ? h->c_lo : nullptr; ea.ld = h->upad[0];
+    ea.targ = h->c_targ;
+    launch_expand_chunk(ea, h->s_main);
+    GGD_CUDA(cudaGetLastError());
+    GGD_TRY(run_chunk(h, c->n_samples, h->c_in, h->c_targ, nullptr, nullptr, true));
+    h->stats.launches += 1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev_c0, h->ev_c1);
+    h->stats.h2d_ms = ms; h->stats.h2d_bytes = (nf + nt) * 4 + (size_t)c->n_samples * sizeof(int);
     return GGD_OK;
 }
 

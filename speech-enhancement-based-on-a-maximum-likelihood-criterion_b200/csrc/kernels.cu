@@ -42,6 +42,46 @@ void launch_split_rows(const float *src, int rows, int cols, bf16 *hi, bf16 *lo,
 }
 
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float be_word_zscore(unsigned int w, float mean, float dvar)
+{
+    const float v = __uint_as_float(__byte_perm(w, 0, 0x0123));      // big-endian float32 (Interface.cc:744, SwapBytes)
+    return __fmul_rn(__fsub_rn(v, mean), dvar);                      // two roundings, exactly as the host loader (no FMA)
+}
+
+__global__ void __launch_bounds__(256) expand_chunk_kernel(const ExpandArgs a)
+{
+    const int r = blockIdx.x;
+    const int f0 = a.first[r];
+    const int in_dim = a.fea_dim * a.ctx;
+    const unsigned int *src = a.fea_rec + (size_t)f0 * (2 + a.fea_dim);
+    for (int e = threadIdx.x; e < a.ld; e += blockDim.x) {
+        float v = 0.0f;
+        if (e < in_dim) {
+            const int c = e / a.fea_dim, j = e - c * a.fea_dim;
+            v = be_word_zscore(__ldg(src + (size_t)c * (2 + a.fea_dim) + 2 + j), __ldg(a.mean + j), __ldg(a.dvar + j));
+            if (a.in32) a.in32[(size_t)r * in_dim + e] = v;
+        }
+        if (a.in_hi) {
+            bf16 h, l;
+            split_bf16(v, h, l);
+            a.in_hi[(size_t)r * a.ld + e] = h;
+            a.in_lo[(size_t)r * a.ld + e] = l;
+        }
+    }
+    const unsigned int *ts = a.targ_rec + (size_t)(f0 + a.targ_offset) * (2 + a.D) + 2;
+    for (int j = threadIdx.x; j < a.D; j += blockDim.x) {
+        const int k = j % a.fea_dim;                                  // targets use the NOISY mean / dVar too (:807-808)
+        a.targ[(size_t)r * a.D + j] = be_word_zscore(__ldg(ts + j), __ldg(a.mean + k), __ldg(a.dvar + k));
+    }
+}
+
+void launch_expand_chunk(const ExpandArgs &a, cudaStream_t s)
+{
+    if (a.samples <= 0) return;
+    expand_chunk_kernel<<<a.samples, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
 // |e|^p: exact for the two named configurations (beta = 2, beta = 1); otherwise exp2(p*log2 a) with the hardware
 // approximations (relative error ~1e-6 * p*|log2 a|, far inside the 1e-3 tolerance; the reference uses powf).
 __device__ __forceinline__ float pow_abs(float a, float p)

@@ -20,6 +20,21 @@ struct StepCtl {
 // fp32 [rows][cols] -> bf16 hi / lo [rows][ld] (columns >= cols are zeroed)
 void launch_split_rows(const float *src, int rows, int cols, bf16 *hi, bf16 *lo, int ld, cudaStream_t s);
 
+// Device-side restatement of the arithmetic of Interface::Readchunk (Interface.cc:735-838): raw big-endian pfile records
+// -> byte swap, z-score with the noisy-speech mean / reciprocal std on BOTH streams (:760-766, :804-810), context expansion
+// (:778-785), target frame selection (:822-827) and the bf16 hi/lo operand split of the net input, in one pass.
+struct ExpandArgs {
+    const unsigned int *fea_rec, *targ_rec;   // [need][2 + fea_dim] / [need][2 + D] big-endian words
+    const int *first;                         // [samples] first context frame of every (already shuffled) row
+    const float *mean, *dvar;                 // [fea_dim]
+    int samples, fea_dim, ctx, targ_offset, D;
+    float *in32;                              // [samples][fea_dim*ctx] fp32 (validation path) or NULL
+    bf16 *in_hi, *in_lo;                      // [samples][ld] (tensor path) or NULL
+    int ld;
+    float *targ;                              // [samples][D]
+};
+void launch_expand_chunk(const ExpandArgs &a, cudaStream_t s);
+
 struct LossArgs {
     const StepCtl *ctl;
     const float *out;   // [M][ldo] network output of this bunch (fp32)

@@ -41,7 +41,14 @@ int main(int argc, char **argv)
     H.shuffle(order);
     // double buffer; the buffers are allocated once at full chunk size so that the library can pin them
     std::vector<float> in[2], tg[2];
-    for (int k = 0; k < 2; k++) { in[k].reserve((size_t)p.traincache * p.layersizes[0]); tg[k].reserve((size_t)p.traincache * p.layersizes[p.numlayers - 1]); }
+    // device-side loader (default): the loader thread only reads the raw records and builds the row -> first-frame map;
+    // byte swap, z-score, context expansion and target selection run on the GPU (ggd_train_raw).  host_loader=1 restores
+    // the reference's division of labour (everything on the CPU, ggd_train).
+    const bool raw = !p.host_loader;
+    std::vector<unsigned> rfea[2], rtg[2];
+    std::vector<int> first[2];
+    int need[2] = {0, 0};
+    if (!raw) for (int k = 0; k < 2; k++) { in[k].reserve((size_t)p.traincache * p.layersizes[0]); tg[k].reserve((size_t)p.traincache * p.layersizes[p.numlayers - 1]); }
     int samples[2] = {0, 0};
     std::mutex mu;
     std::condition_variable cv;
@@ -53,7 +60,8 @@ int main(int argc, char **argv)
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return i - consumed < 2; });
             }
-            const int n = H.read_chunk(order[i], false, in[i & 1], tg[i & 1]);
+            const int n = raw ? H.read_chunk_raw(order[i], rfea[i & 1], rtg[i & 1], first[i & 1], &need[i & 1])
+                              : H.read_chunk(order[i], false, in[i & 1], tg[i & 1]);
             std::lock_guard<std::mutex> lk(mu);
             samples[i & 1] = n;
             if (n < 0) load_failed = true;
@@ -71,7 +79,14 @@ int main(int argc, char **argv)
         }
         H.logf("Starting chunk %d of %d containing %d samples.\n", i + 1, H.total_chunks, samples[i & 1]);
         if (samples[i & 1] % p.bunchsize) printf("this bunch has only %d samples and is ignored.\n", samples[i & 1] % p.bunchsize);
-        if (ggd_train(net, samples[i & 1], in[i & 1].data(), tg[i & 1].data()) != GGD_OK) { H.logf("%s\n", ggd_last_error()); rc = 1; }
+        if (raw) {
+            ggd_raw_chunk c;
+            c.fea_records = rfea[i & 1].data(); c.targ_records = rtg[i & 1].data();
+            c.n_frames = need[i & 1]; c.n_samples = samples[i & 1]; c.sample_first_frame = first[i & 1].data();
+            c.fea_dim = p.fea_dim; c.fea_context = p.fea_context; c.targ_offset = p.targ_offset;
+            c.mean = H.mean_ptr(); c.dvar = H.dvar_ptr();
+            if (ggd_train_raw(net, &c) != GGD_OK) { H.logf("%s\n", ggd_last_error()); rc = 1; }
+        } else if (ggd_train(net, samples[i & 1], in[i & 1].data(), tg[i & 1].data()) != GGD_OK) { H.logf("%s\n", ggd_last_error()); rc = 1; }
         std::lock_guard<std::mutex> lk(mu);
         consumed = i + 1;
         cv.notify_all();

@@ -73,6 +73,7 @@ bool Host::init(int argc, char **argv)
         }
         else if (k == "precision") p.precision = (v == "fp32" || v == "1") ? 1 : 0;
         else if (k == "no_graph") p.no_graph = atoi(v.c_str());
+        else if (k == "host_loader") p.host_loader = atoi(v.c_str());
         // anything else (e.g. numlayers=) is silently ignored, as in the reference
     }
     if (!(fp_log = fopen(p.log_file.c_str(), "wt"))) { printf("can not open output log file: %s\n", p.log_file.c_str()); return false; }
@@ -297,6 +298,45 @@ int Host::read_chunk(int idx, bool cv, std::vector<float> &in, std::vector<float
             processed += n;
         }
     }
+    return samples;
+}
+
+// Readchunk (Interface.cc:719-838) without its arithmetic: raw records + row -> first-frame map (see interface.h)
+int Host::read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<unsigned> &targ_rec, std::vector<int> &first, int *need_out)
+{
+    const int D = p.layersizes[p.numlayers - 1], fd = p.fea_dim, ctx = p.fea_context;
+    int need, samples;
+    if (idx == total_chunks - 1) { need = frames_before_sent[sent_en] - chunk_st[idx]; samples = total_samples - p.traincache * idx; }
+    else { samples = p.traincache; need = chunk_st[idx + 1] - chunk_st[idx]; }
+    std::vector<int> order(samples);
+    for (int i = 0; i < samples; i++) order[i] = i;
+    shuffle(order);                                                        // per-sample shuffle, :750-754
+    first.assign(samples, 0);
+    for (int stream = 0; stream < 2; stream++) {
+        const int dim = stream == 0 ? fd : D;
+        FILE *fp = stream == 0 ? fp_data : fp_targ;
+        std::vector<unsigned> &raw = stream == 0 ? fea_rec : targ_rec;
+        const long rec = 4L * (dim + 2);
+        if (fseek(fp, kPfileHeader + (long)chunk_st[idx] * rec, SEEK_SET) != 0) { logf("%s pfile cannot fseek to chunk %d.\n", stream ? "targ" : "data", idx); return -1; }
+        raw.resize((size_t)need * (dim + 2));
+        if (fread(raw.data(), rec, need, fp) != (size_t)need) { logf("%s pfile short read in chunk %d.\n", stream ? "targ" : "data", idx); return -1; }
+    }
+    int cur_sent = (int)bswap32(fea_rec[0]);
+    int processed = 0, cur_frame = chunk_st[idx], cur_sample = 0;
+    while (processed != need) {
+        int n;
+        if (frames_before_sent[cur_sent] > need + chunk_st[idx]) n = need - processed;
+        else n = frames_before_sent[cur_sent] - cur_frame;
+        for (int j = 0; j <= n - ctx; j++) {
+            if (cur_sample >= samples) break;
+            first[order[cur_sample]] = processed + j;                      // rows = frames j..j+ctx-1, target = frame j+targ_offset
+            cur_sample++;
+        }
+        cur_frame = frames_before_sent[cur_sent];
+        cur_sent++;
+        processed += n;
+    }
+    *need_out = need;
     return samples;
 }
 

@@ -23,6 +23,7 @@ struct Params {                          // struct WorkPara, Interface.h:31-69
     // extensions of this implementation (ignored by the reference, which skips unknown names)
     int precision = 0;      // precision=fp32 selects the CUDA-core validation path
     int no_graph = 0;
+    int host_loader = 0;    // host_loader=1: z-score / context expansion on the CPU (ggd_train) instead of the device-side loader
 };
 
 class Host {
@@ -35,6 +36,11 @@ public:
     void shuffle(std::vector<int> &v);                        // GetRandIndex, Interface.cc:975-986
     // fills in/targ (resized to samples*dim) with chunk `idx`; returns the number of samples, <0 on error
     int read_chunk(int idx, bool cv, std::vector<float> &in, std::vector<float> &targ);
+    // the same chunk for the device-side loader (ggd_train_raw): the raw big-endian records as they lie in the pfiles and,
+    // per shuffled net-input row, its first context frame inside the chunk; consumes the same random numbers as read_chunk
+    int read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<unsigned> &targ_rec, std::vector<int> &first, int *need_out);
+    const float *mean_ptr() const { return mean.data(); }
+    const float *dvar_ptr() const { return dvar.data(); }
     bool write_weights();                                     // Interface::Writeweights, Interface.cc:484-516
     void logf(const char *fmt, ...);
 

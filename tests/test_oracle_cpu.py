@@ -315,3 +315,23 @@ def test_cv_metrics_definitions(oracle):
     assert abs(net.cv_abserr(x, t) - np.abs(out - t).sum() / 4) < 1e-3
     ll = 19 * 4 * math.log(1.5 / (2 * math.gamma(1 / 1.5))) - 19 * np.log(al).sum() - (np.abs((t - out) / al) ** 1.5).sum()
     assert abs(net.cv_loglik(x, t) - ll) < 2e-3 * abs(ll)
+
+
+def test_raw_chunk_helper_matches_loader(oracle=None):
+    """read_chunk_raw (inputs of the device-side loader) + the loader arithmetic in numpy == read_chunk, bit for bit"""
+    from oracle import oracle as O
+    fea, tg, nrm = (os.path.join(GOLDEN, f) for f in ("train_noisy.pfile", "train_clean.pfile", "train_noisy.norm"))
+    la = O.PfileLoader(fea, tg, nrm, 257, 7, 3, 500, 27870775)
+    lb = O.PfileLoader(fea, tg, nrm, 257, 7, 3, 500, 27870775)
+    sent_en = len(la.sent_end) - 1
+    starts, total = la.chunk_info(0, sent_en)
+    for idx in range(len(starts)):
+        ind, tgt = la.read_chunk(starts, total, sent_en, idx)
+        frec, trec, first = lb.read_chunk_raw(starts, total, sent_en, idx)
+        x = frec[:, 2:].copy().byteswap().view(np.float32)
+        x = ((x - lb.mean).astype(np.float32) * lb.dvar).astype(np.float32)
+        t = trec[:, 2:].copy().byteswap().view(np.float32)
+        t = ((t - lb.mean).astype(np.float32) * lb.dvar).astype(np.float32)
+        got_in = np.stack([x[f:f + 7].reshape(-1) for f in first])
+        got_tg = np.stack([t[f + 3] for f in first])
+        assert np.array_equal(got_in, ind) and np.array_equal(got_tg, tgt)

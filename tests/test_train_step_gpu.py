@@ -188,3 +188,34 @@ def test_chunk_ragged_bunch_production_path(pkg, oracle, M, MLflag, beta):
         assert rel_err(Wg[l], Wo[l]) < 1e-3
         assert rel_err(bg[l], bo[l]) < 1e-3
         assert rel_err(Wg[l] - W[l], Wo[l] - W[l]) < 2e-3, l
+
+
+def test_device_loader_equals_host_loader(pkg, oracle):
+    """ggd_train_raw (byte swap, z-score, context expansion, target selection and operand split on the GPU
+    from the raw pfile records) must give BIT-identical training to ggd_train on the arrays expanded by the restated host
+    loader, chunk by chunk, on the reference's bundled pfiles with finetune.pl's settings (ctx 7, offset 3, seed 27870775)"""
+    import os
+    from conftest import GOLDEN
+    O = oracle
+    fea, tg, nrm = (os.path.join(GOLDEN, f) for f in ("train_noisy.pfile", "train_clean.pfile", "train_noisy.norm"))
+    layersizes, M, cache = [7 * 257, 96, 257], 128, 600
+    W, b = O.init_weights(layersizes, seed=4)
+    nets = [pkg.BP_GPU(0, 0, 3, layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1) for _ in range(2)]
+    loaders = [O.PfileLoader(fea, tg, nrm, 257, 7, 3, cache, 27870775) for _ in range(2)]
+    sent_en = len(loaders[0].sent_end) - 1
+    starts, total = loaders[0].chunk_info(0, sent_en)
+    assert len(starts) >= 2
+    for idx in range(len(starts)):
+        ind, tgt = loaders[0].read_chunk(starts, total, sent_en, idx)
+        frec, trec, first = loaders[1].read_chunk_raw(starts, total, sent_en, idx)
+        assert first.size == ind.shape[0]
+        nets[0].train(ind.shape[0], ind, tgt)
+        nets[1].train_raw(frec, trec, first, 257, 7, 3, loaders[1].mean, loaders[1].dvar)
+        assert np.array_equal(nets[0].losses(), nets[1].losses()), idx
+    (Wa, ba), (Wb, bb) = nets[0].returnWeights(), nets[1].returnWeights()
+    for u, v in zip(Wa + ba, Wb + bb):
+        assert np.array_equal(u, v)
+    assert np.array_equal(nets[0].alpha(), nets[1].alpha())
+    # argument checking: a row that would read past the chunk is refused
+    with pytest.raises(Exception):
+        nets[1].train_raw(frec, trec, np.array([frec.shape[0] - 3], np.int32), 257, 7, 3, loaders[1].mean, loaders[1].dvar)
