@@ -749,22 +749,21 @@ static int set_ctl(ggd_handle *h, const float *d_in, const float *d_targ)
 static int pin_host(ggd_handle *h, const float *src, size_t bytes)
 {
     // pin the caller's (reused) buffer once so that the copy is a real DMA (the reference hands us pageable memory)
-    if ((h->cfg.flags & GGD_FLAG_PIN_HOST) && bytes >= (1u << 20) && h->pinned.find(src) == h->pinned.end()) {
-        cudaError_t e = cudaHostRegister(const_cast<float *>(src), bytes, cudaHostRegisterDefault);
-        if (e == cudaSuccess) h->pinned[src] = bytes;
-        else { cudaGetLastError(); h->pinned[src] = 0; }
-    }
+    if (!(h->cfg.flags & GGD_FLAG_PIN_HOST) || bytes < (1u << 20)) return GGD_OK;
+    auto it = h->pinned.find(src);
+    if (it != h->pinned.end() && (it->second == 0 || it->second >= bytes)) return GGD_OK;   // pinned large enough (or unpinnable)
+    // a reused buffer may carry a LARGER chunk than the one it was first seen with (the chunks of an epoch differ in size
+    // and come in shuffled order): a copy that spans registered and unregistered pages is an error, so re-register
+    if (it != h->pinned.end()) cudaHostUnregister(const_cast<float *>(src));
+    cudaError_t e = cudaHostRegister(const_cast<float *>(src), bytes, cudaHostRegisterDefault);
+    if (e == cudaSuccess) h->pinned[src] = bytes;
+    else { cudaGetLastError(); h->pinned[src] = 0; }
     return GGD_OK;
 }
 
 static int upload(ggd_handle *h, const float *src, float *dst, size_t bytes)
 {
-    // pin the caller's (reused) buffer once so that the copy is a real DMA (the reference hands us pageable memory)
-    if ((h->cfg.flags & GGD_FLAG_PIN_HOST) && bytes >= (1u << 20) && h->pinned.find(src) == h->pinned.end()) {
-        cudaError_t e = cudaHostRegister(const_cast<float *>(src), bytes, cudaHostRegisterDefault);
-        if (e == cudaSuccess) h->pinned[src] = bytes;
-        else { cudaGetLastError(); h->pinned[src] = 0; }
-    }
+    GGD_TRY(pin_host(h, src, bytes));
     GGD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_main));
     return GGD_OK;
 }
@@ -1121,8 +1120,8 @@ int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *c)
     GGD_TRY(grow(&h->r_targ, &h->r_cap_targ, nt));
     GGD_TRY(grow(&h->r_first, &h->r_cap_first, (size_t)c->n_samples));
     GGD_TRY(grow(&h->r_norm, &h->r_cap_norm, (size_t)2 * c->fea_dim));
-    GGD_TRY(pin_host(h, reinterpret_cast<const float *>(c->fea_records), nf * 4));
-    GGD_TRY(pin_host(h, reinterpret_cast<const float *>(c->targ_records), nt * 4));
+    // (the record buffers are NOT pinned: their size varies from chunk to chunk, so a caller is free to reallocate them,
+    // and a registration that outlives its allocation corrupts the address space; the raw copy is 4x smaller anyway)
     GGD_CUDA(cudaEventRecord(h->ev_c0, h->s_main));
     GGD_CUDA(cudaMemcpyAsync(h->r_fea, c->fea_records, nf * 4, cudaMemcpyHostToDevice, h->s_main));
     GGD_CUDA(cudaMemcpyAsync(h->r_targ, c->targ_records, nt * 4, cudaMemcpyHostToDevice, h->s_main));

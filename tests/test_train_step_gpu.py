@@ -219,3 +219,26 @@ def test_device_loader_equals_host_loader(pkg, oracle):
     # argument checking: a row that would read past the chunk is refused
     with pytest.raises(Exception):
         nets[1].train_raw(frec, trec, np.array([frec.shape[0] - 3], np.int32), 257, 7, 3, loaders[1].mean, loaders[1].dvar)
+
+
+def test_reused_host_buffer_growing_chunks(pkg, oracle):
+    """GGD_FLAG_PIN_HOST with a REUSED host buffer whose chunks grow (an epoch's chunks differ in size and come in shuffled
+    order: BPtrain.cc reuses indata/targ): the pinned range must follow, and the piece-wise upload must stay correct"""
+    O = oracle
+    layersizes, M = [300, 64, 40], 128
+    W, b, x, t = make_case(O, layersizes, M * 150, 41)     # 300*4*128*150 = 23 MB: above the 1 MB pinning threshold
+    buf_x = np.zeros_like(x); buf_t = np.zeros_like(t)
+    net = pkg.BP_GPU(0, 0, 3, layersizes, M, 0.05, 0.9, 1e-5, W, b, 1.5, 1, flags=pkg.FLAG_PIN_HOST)
+    orc = O.OracleNet(layersizes, M, 0.05, 0.9, 1e-5, 1.5, 1, W, b)
+    pos = 0
+    for nb in (20, 130):                                    # small chunk first, then a much larger one in the same buffer
+        n = nb * M
+        buf_x[:n] = x[pos:pos + n]; buf_t[:n] = t[pos:pos + n]
+        net.train(n, buf_x[:n], buf_t[:n])
+        lo, _ = orc.train(x[pos:pos + n], t[pos:pos + n])
+        assert np.max(np.abs(net.losses() - lo) / np.abs(lo)) < 5e-3
+        pos += n
+    Wg, _ = net.returnWeights()
+    Wo, _ = orc.weights()
+    for l in range(2):
+        assert rel_err(Wg[l], Wo[l]) < 1e-3
