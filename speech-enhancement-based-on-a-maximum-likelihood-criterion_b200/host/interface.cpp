@@ -395,6 +395,19 @@ int bph_read_chunk(void *p, int idx, int cv, float *in, float *targ)
     memcpy(targ, b.data(), b.size() * sizeof(float));
     return n;
 }
+// raw chunk for the device-side loader: fea / targ must hold need*(2+dim) words (need <= max_frames), first >= samples ints
+int bph_read_chunk_raw(void *p, int idx, unsigned *fea, unsigned *targ, int *first, int max_frames, int *need)
+{
+    bphost::Host *h = (bphost::Host *)p;
+    std::vector<unsigned> a, b;
+    std::vector<int> f;
+    const int n = h->read_chunk_raw(idx, a, b, f, need);
+    if (n < 0 || *need > max_frames) return -1;
+    memcpy(fea, a.data(), a.size() * sizeof(unsigned));
+    memcpy(targ, b.data(), b.size() * sizeof(unsigned));
+    memcpy(first, f.data(), f.size() * sizeof(int));
+    return n;
+}
 const float *bph_weights(void *p, int l) { return ((bphost::Host *)p)->W[l].data(); }
 const float *bph_bias(void *p, int l) { return ((bphost::Host *)p)->b[l].data(); }
 int bph_write_weights(void *p) { return ((bphost::Host *)p)->write_weights() ? 0 : -1; }

@@ -90,6 +90,7 @@ def _host_lib():
     L.bph_chunk_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.bph_shuffle.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
     L.bph_read_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, oracle_PF, oracle_PF]
+    L.bph_read_chunk_raw.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.bph_weights.restype = oracle_PF
     L.bph_weights.argtypes = [C.c_void_p, C.c_int]
     L.bph_write_weights.argtypes = [C.c_void_p]
@@ -335,3 +336,37 @@ def test_raw_chunk_helper_matches_loader(oracle=None):
         got_in = np.stack([x[f:f + 7].reshape(-1) for f in first])
         got_tg = np.stack([t[f + 3] for f in first])
         assert np.array_equal(got_in, ind) and np.array_equal(got_tg, tgt)
+
+
+@pytest.mark.parametrize("traincache", [102400, 500])
+def test_host_raw_chunk_reader(oracle, tmp_path, traincache):
+    """host/interface.cpp: read_chunk_raw (what the drop-in executable feeds ggd_train_raw) against the loader restatement:
+    same raw records, same shuffled row -> first-frame map, same random numbers consumed as the expanding reader"""
+    L = _host_lib()
+    ls = [1799, 32, 16, 257]
+    W, b = oracle.init_weights(ls, seed=3)
+    init = str(tmp_path / "init.wts")
+    oracle.write_wts(init, ls, W, b)
+    kw = _flags(tmp_path, init, traincache=traincache)
+    h = L.bph_create(*_argv(kw))
+    assert h
+    nch, ns = C.c_int(), C.c_int()
+    assert L.bph_chunk_info(h, b"0-7", 0, C.byref(nch), C.byref(ns)) == 0
+    ld = oracle.PfileLoader(kw["fea_file"], kw["targ_file"], kw["norm_file"], 257, 7, 3, traincache, SEED)
+    st, tot = ld.chunk_info(0, 7)
+    assert (nch.value, ns.value) == (len(st), tot)
+    order = list(range(len(st)))
+    oracle.rand_index(order, ld.rng)
+    idx = (C.c_int * len(st))(*range(len(st)))
+    L.bph_shuffle(h, idx, len(st))
+    assert list(idx) == order
+    maxf = 4000
+    fea = np.zeros((maxf, 259), np.uint32); tg = np.zeros((maxf, 259), np.uint32); first = np.zeros(traincache, np.int32)
+    need = C.c_int()
+    for ci in order:
+        n = L.bph_read_chunk_raw(h, ci, fea.ctypes.data, tg.ctypes.data, first.ctypes.data, maxf, C.byref(need))
+        fr, tr, f0 = ld.read_chunk_raw(st, tot, 7, ci)
+        assert n == f0.size and need.value == fr.shape[0]
+        assert np.array_equal(first[:n], f0)
+        assert np.array_equal(fea[:need.value, 2:], fr[:, 2:]) and np.array_equal(tg[:need.value, 2:], tr[:, 2:])
+    L.bph_destroy(h)
