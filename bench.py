@@ -342,7 +342,7 @@ def main():
                 "peak_source": peaks["src"]}
         if dom == "dw_update":
             roof["kernel"] = "dw_persist_kernel (dW GEMM + momentum update of all layers; 16 B/param algorithmic)"
-            tp = os.path.join(ROOT, "profiles", "r01f_dw_persist_traffic.json")
+            tp = os.path.join(ROOT, "profiles", "r01g_dw_persist_traffic.json")
             if os.path.exists(tp) and ls == [1799, 2048, 2048, 2048, 257]:
                 tj = json.load(open(tp))
                 roof["traffic"] = tj["traffic_bytes_per_launch"]
