@@ -375,12 +375,17 @@ __global__ void __launch_bounds__(k2::NTHREADS, 1) reduce_update_kernel(const Dp
                 mbar_wait_bounded(&done[s], (it / STG) & 1, hang, 10, it);
                 const uint8_t *st = ring + s * SB;
                 const int c0 = tr.nt * TN, c1 = tr.kt * 64 + e8 * ROWS;
-                tma_store_2d_hint(&L->w_map, st, c0, c1, pol_stream);
+                tma_store_2d_hint(&L->w_map, st, c0, c1, gp->w_f32 ? pol_keep : pol_stream);
                 tma_store_2d_hint(&L->d_map, st + F32, c0, c1, pol_stream);
-                const uint8_t *sh = st + (2 + world) * F32;
-                for (int p = 0; p < world; p++) {
-                    tma_store_2d_hint(&L->hi_map[p], sh, c0, c1, pol_keep);
-                    tma_store_2d_hint(&L->lo_map[p], sh + B16, c0, c1, pol_keep);
+                if (gp->w_f32) {
+                    for (int p = 0; p < world; p++)
+                        if (p != rank) tma_store_2d_hint(&L->wp_map[p], st, c0, c1, pol_keep);   // the weights themselves, to every peer
+                } else {
+                    const uint8_t *sh = st + (2 + world) * F32;
+                    for (int p = 0; p < world; p++) {
+                        tma_store_2d_hint(&L->hi_map[p], sh, c0, c1, pol_keep);
+                        tma_store_2d_hint(&L->lo_map[p], sh + B16, c0, c1, pol_keep);
+                    }
                 }
                 tma_store_commit();
                 if (prev_s >= 0) {
@@ -438,6 +443,7 @@ __global__ void __launch_bounds__(k2::NTHREADS, 1) reduce_update_kernel(const Dp
             w.x += d.x; w.y += d.y; w.z += d.z; w.w += d.w;
             *sw = w;
             *sd = d;
+            if (!gp->w_f32) {
             const __nv_bfloat162 h01 = __floats2bfloat162_rn(w.x, w.y), h23 = __floats2bfloat162_rn(w.z, w.w);
             const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
             const __nv_bfloat162 l01 = __floats2bfloat162_rn(w.x - f01.x, w.y - f01.y), l23 = __floats2bfloat162_rn(w.z - f23.x, w.w - f23.y);
@@ -447,6 +453,7 @@ __global__ void __launch_bounds__(k2::NTHREADS, 1) reduce_update_kernel(const Dp
             uint8_t *sh = st + (2 + world) * F32;
             *(reinterpret_cast<uint2 *>(sh + (size_t)row * TN * 2) + lane) = hv;
             *(reinterpret_cast<uint2 *>(sh + B16 + (size_t)row * TN * 2) + lane) = lv;
+            }
             fence_async_proxy();
             __syncwarp();
             if (lane == 0) mbar_arrive(&done[s]);

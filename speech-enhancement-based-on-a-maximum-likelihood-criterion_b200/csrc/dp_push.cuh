@@ -30,6 +30,7 @@ struct DpxLayer {
     CUtensorMap b_hi, b_lo;   // activations of the layer below, bf16 [rows][Kp], box {64, 64}, 128-byte swizzle
     CUtensorMap w_map, d_map; // local fp32 weights / momentum [Kp][Np], box {128 n, 8 k}
     CUtensorMap hi_map[DPX_MAX], lo_map[DPX_MAX];   // bf16 shadows of EVERY rank [Kp][Np], box {128 n, 8 k}
+    CUtensorMap wp_map[DPX_MAX];                    // fp32 weights of EVERY rank (w_f32 mode: the updated weights themselves are broadcast)
     const bf16 *dx_hi, *dx_lo;
     float *b, *db;
     int Kp, Np, N, k_tiles, tile_base, b_rows_from_ctl, bias_off, pad;
@@ -51,6 +52,7 @@ struct DpxArgs {
     int own_begin[DPX_MAX + 1];      // owner o holds tiles [own_begin[o], own_begin[o+1])
     int nlayers, total_tiles, world, rank, nbias, rows_per_bunch, M;
     int k2_stages, k2_stage_bytes;
+    int w_f32, pad4;                 // 1: broadcast fp32 weights into every rank's master array instead of bf16 shadows
     float mom, lr, Mg;
 };
 

@@ -204,15 +204,20 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                     const uint8_t *src = wd_ring + ws * WD_STAGE;
                     const int c0 = tr.nt * TN, c1 = tr.kt * TK + qt * WD_ROWS;
                     if (gp->l2_hints) {
-                        tma_store_2d_hint(&L->w_map, src, c0, c1, pol_stream);
+                        // without shadows the fp32 weights themselves are what the next step's GEMMs read: keep them in L2
+                        tma_store_2d_hint(&L->w_map, src, c0, c1, gp->shadows ? pol_stream : pol_keep);
                         tma_store_2d_hint(&L->d_map, src + WD_F32, c0, c1, pol_stream);
-                        tma_store_2d_hint(&L->hi_map, src + 2 * WD_F32, c0, c1, pol_keep);
-                        tma_store_2d_hint(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1, pol_keep);
+                        if (gp->shadows) {
+                            tma_store_2d_hint(&L->hi_map, src + 2 * WD_F32, c0, c1, pol_keep);
+                            tma_store_2d_hint(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1, pol_keep);
+                        }
                     } else {
                         tma_store_2d(&L->w_map, src, c0, c1);
                         tma_store_2d(&L->d_map, src + WD_F32, c0, c1);
-                        tma_store_2d(&L->hi_map, src + 2 * WD_F32, c0, c1);
-                        tma_store_2d(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1);
+                        if (gp->shadows) {
+                            tma_store_2d(&L->hi_map, src + 2 * WD_F32, c0, c1);
+                            tma_store_2d(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1);
+                        }
                     }
                     tma_store_commit();
                     if (prev_ws >= 0) {
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
         // ===== update warps (8): quadrant q = accumulator lanes [32q, 32q+32); `h` = which 8 of a stage's 16 rows =====
         const int e = warp - 2, q = warp & 3, h = e >> 2;
         const float mom = gp->mom, lr = gp->lr, inv_mg = 1.0f / gp->Mg;
+        const bool shadows = gp->shadows != 0;
         TileRef tr = decode_tile(gp, t0);
         for (int t = t0, it = 0; t < t1; t++, it++) {
             const DwpLayer *L = tr.L;
@@ -308,10 +314,12 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                     const float wn = dd + ww;
                     sw[x * TN] = wn;
                     sd[x * TN] = dd;
-                    bf16 hv, lv;
-                    split_bf16(wn, hv, lv);
-                    shi[x * TN] = hv;
-                    slo[x * TN] = lv;
+                    if (shadows) {
+                        bf16 hv, lv;
+                        split_bf16(wn, hv, lv);
+                        shi[x * TN] = hv;
+                        slo[x * TN] = lv;
+                    }
                 }
                 fence_async_proxy();      // the stage is read by the TMA store engine next
                 __syncwarp();

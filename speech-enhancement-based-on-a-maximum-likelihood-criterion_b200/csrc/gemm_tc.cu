@@ -17,13 +17,28 @@ namespace ggd {
 constexpr int BK = 64;                 // reduction elements per stage (128 bytes of bf16: one swizzle row)
 constexpr int TILE_I = 128;            // UMMA M
 constexpr int A_TILE = TILE_I * BK * 2;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 192;           // shadow mode
+constexpr int CONV_GROUPS = 1;           // B_F32: converter groups of 4 warps alternating over the k-blocks (measured: 1 group + a deep
+                                        // raw ring beats 2 groups with separate A / B rings: 123.6 vs 131 us per step)
+constexpr int NTHREADS_F32 = 192 + 128 * (CONV_GROUPS - 1);
 
-template <int BN> struct TileCfg {
+// B_F32: the B operand (the weight matrix) is read as fp32 straight from the MASTER weights and split into bf16 hi/lo
+// inside the kernel by the epilogue warps (idle during the main loop): no bf16 shadow copy of the weights has to be
+// maintained by the update kernel (4 B/param less HBM traffic per step), same operand bytes through TMA.
+template <int BN, bool B_F32 = false> struct TileCfg {
     static constexpr int B_TILE = BN * BK * 2;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int STAGES = (BN == 128) ? 3 : 4;
-    static constexpr int SMEM = STAGES * STAGE + 1024;
+    static constexpr int STAGES = (BN == 128) ? 3 : 4;             // shadow mode: A and B of a k-block share one stage
+    // B_F32: three rings -- A (TMA, hi+lo), converted B (bf16 hi+lo written by the converter warps), raw fp32 B (TMA).
+    // The activation operand is 2/3 of the bytes a CTA streams, so its ring stays as deep as in shadow mode.
+    // B_F32: the operand stages keep the interleaved A|B layout (B = bf16 hi+lo written by the converter warps) with one
+    // stage less, and a separate raw ring receives the fp32 weight tiles by TMA.
+    static constexpr int A_ST = B_F32 ? ((BN == 128) ? 2 : 3) : STAGES;
+    static constexpr int B_ST = A_ST;
+    static constexpr int RAW_TILE = BN * BK * 4;                    // fp32 [BN rows][64], unswizzled
+    static constexpr int RAW_STAGES = B_F32 ? ((BN == 128) ? 2 : 4) : 0;
+    static constexpr int SMEM = A_ST * STAGE + RAW_STAGES * RAW_TILE + 1024;
+    static_assert(SMEM + 12 * 1024 <= 227 * 1024, "dynamic + static shared memory (barriers, loss tile) must fit one SM");
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -239,16 +254,22 @@ __device__ __forceinline__ void epilogue_loss16(const GemmArgs &g, int i, int j,
     asm volatile("bar.sync 1, 128;" ::: "memory");   // tile / part / colscale are reused by the next 16-column chunk
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int EPI, bool B_F32>
+__global__ void __launch_bounds__(B_F32 ? NTHREADS_F32 : NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GemmArgs g)
 {
-    using Cfg = TileCfg<BN>;
-    constexpr int B_TILE = Cfg::B_TILE, STAGE = Cfg::STAGE, STAGES = Cfg::STAGES;
+    using Cfg = TileCfg<BN, B_F32>;
+    constexpr int B_TILE = Cfg::B_TILE, STAGE = Cfg::STAGE, A_ST = Cfg::A_ST, B_ST = Cfg::B_ST;
+    constexpr int RAW_TILE = Cfg::RAW_TILE, RAW_STAGES = B_F32 ? Cfg::RAW_STAGES : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    // operand stage addresses: shadow mode interleaves A and B per stage; B_F32 keeps an A ring, a converted-B ring, a raw ring
+    auto a_stage = [&](int it) -> uint8_t * { return smem + (it % A_ST) * STAGE; };
+    auto b_stage = [&](int it) -> uint8_t * { return smem + (it % B_ST) * STAGE + 2 * A_TILE; };
+    uint8_t *raw_ring = smem + A_ST * STAGE;   // B_F32 only
+    __shared__ __align__(8) uint64_t full_bar[A_ST], empty_bar[A_ST], tmem_full_bar;          // A (and B in shadow mode)
+    __shared__ __align__(8) uint64_t bconv_bar[B_ST], bempty_bar[B_ST], raw_full_bar[RAW_STAGES], raw_empty_bar[RAW_STAGES];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,7 +285,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < A_ST; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < B_ST; s++) { mbar_init(&bconv_bar[s], 4); mbar_init(&bempty_bar[s], 1); }
+            for (int s = 0; s < RAW_STAGES; s++) { mbar_init(&raw_full_bar[s], 1); mbar_init(&raw_empty_bar[s], 4 * CONV_GROUPS); }
             mbar_init(&tmem_full_bar, 1);
             fence_mbar_init();
         }
@@ -286,10 +309,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (lane == 0) {
             // ===== TMA producer =====
             for (int it = 0; it < nkb; it++) {
-                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                const int s = it % A_ST, ph = (it / A_ST) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], STAGE);
-                uint8_t *st = smem + s * STAGE;
+                mbar_expect_tx(&full_bar[s], B_F32 ? 2 * A_TILE : STAGE);
+                uint8_t *st = a_stage(it);
                 const int r0 = (kb0 + it) * BK;
                 if constexpr (!A_MN) {
                     tma_load_2d(st, &tm_a_hi, &full_bar[s], r0, i0 + a_row_off);
@@ -301,8 +324,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         tma_load_2d(st + A_TILE + h * 8192, &tm_a_lo, &full_bar[s], i0 + 64 * h, r0 + a_row_off);
                     }
                 }
-                uint8_t *sb = st + 2 * A_TILE;
-                if constexpr (!B_MN) {
+                uint8_t *sb = b_stage(it);
+                if constexpr (B_F32) {
+                    // fp32 weight tile [BN rows][64 floats] (tm_b_hi is the fp32 map of the master weights)
+                    const int rs = it % RAW_STAGES, rph = (it / RAW_STAGES) & 1;
+                    mbar_wait(&raw_empty_bar[rs], rph ^ 1);
+                    mbar_expect_tx(&raw_full_bar[rs], RAW_TILE);
+                    uint8_t *rw = raw_ring + rs * RAW_TILE;
+                    if constexpr (!B_MN) {
+                        tma_load_2d(rw, &tm_b_hi, &raw_full_bar[rs], r0, j0);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < BN / 64; h++) tma_load_2d(rw + h * 16384, &tm_b_hi, &raw_full_bar[rs], j0 + 64 * h, r0);
+                    }
+                } else if constexpr (!B_MN) {
                     tma_load_2d(sb, &tm_b_hi, &full_bar[s], r0, j0);
                     tma_load_2d(sb + B_TILE, &tm_b_lo, &full_bar[s], r0, j0);
                 } else {
@@ -323,13 +358,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             constexpr uint32_t A_LBO = A_MN ? 8192u : 16u, B_LBO = B_MN ? 8192u : 16u;
             constexpr uint32_t A_KSTEP = A_MN ? 2048u : 32u, B_KSTEP = B_MN ? 2048u : 32u;
             for (int it = 0; it < nkb; it++) {
-                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                const int s = it % A_ST, ph = (it / A_ST) & 1;
+                const int sb = it % B_ST;
                 mbar_wait(&full_bar[s], ph);
+                if constexpr (B_F32) mbar_wait(&bconv_bar[sb], (it / B_ST) & 1);
                 tc_fence_after();
                 if (it == 0) stamp(g, 3);
                 if (it == nkb - 1) stamp(g, 4);
-                const uint32_t a_hi = smem_u32(smem + s * STAGE), a_lo = a_hi + A_TILE;
-                const uint32_t b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + B_TILE;
+                const uint32_t a_hi = smem_u32(a_stage(it)), a_lo = a_hi + A_TILE;
+                const uint32_t b_hi = smem_u32(b_stage(it)), b_lo = b_hi + B_TILE;
 #pragma unroll
                 for (int k = 0; k < BK / 16; k++) {
                     const uint64_t dah = make_smem_desc(a_hi + k * A_KSTEP, A_LBO, 1024);
@@ -341,14 +378,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     umma_bf16(tmem, dah, dbh, idesc, 1);
                 }
                 umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs retire
+                if constexpr (B_F32) umma_commit(&bempty_bar[sb]);
             }
             umma_commit(&tmem_full_bar);
             stamp(g, 5);
         }
         __syncwarp();
     } else {
-        // ===== epilogue warps: wait for the accumulator =====
-        if constexpr (EPI == EPI_FWD_LOSS) {
+        // ===== epilogue warps (2..5; with B_F32 also converter group 0) and converter group 1 (warps 6..9, B_F32 only) =====
+        const bool epi_warp = warp < 6;
+        if constexpr (EPI == EPI_FWD_LOSS) if (epi_warp) {
             // targets and biases of this thread's row / first 16-column chunk: requested now, used after the main loop
             const int qq = warp & 3, ii = i0 + qq * 32 + lane, jj = j0 + rank * (BN / S);
             loss_bunch = g.ctl->bunch_idx;
@@ -360,8 +399,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 loss_bs[x] = (jj + x < g.D) ? __ldg(g.bias + jj + x) : 0.0f;
             }
         }
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
+        if constexpr (B_F32) {
+            // ===== weight converter: fp32 tile -> bf16 hi / lo tiles in the SWIZZLE_128B layout the MMA descriptors expect
+            // (row r of 128 bytes, 16-byte chunk c stored at chunk position c ^ (r & 7)) =====
+            // group 0 (warps 2..5) converts the even k-blocks into B stage 0, group 1 (warps 6..9) the odd ones into stage 1:
+            // one conversion (~0.5 us with its barrier round trips) per k-block was the bottleneck of the operand stream
+            static_assert(CONV_GROUPS == 1 || B_ST == 2, "two converter groups <-> two converted-B stages");
+            const int grp = epi_warp ? 0 : 1;
+            const int ct = (threadIdx.x - 64) & 127;               // 0..127 within the group
+            for (int it = 0; it < nkb; it++) {
+                const int sb = it % B_ST, bph = (it / B_ST) & 1;
+                const int rs = it % RAW_STAGES, rph = (it / RAW_STAGES) & 1;
+                // BOTH groups follow EVERY raw stage (full -> empty) although only one converts it: a group that skipped
+                // the other group's fills could be two phases away from a barrier, which a parity wait cannot detect
+                mbar_wait(&raw_full_bar[rs], rph);
+                if (CONV_GROUPS > 1 && (it % CONV_GROUPS) != grp) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_empty_bar[rs]);
+                    continue;
+                }
+                const uint8_t *rw = raw_ring + rs * RAW_TILE;
+                uint8_t *bh = b_stage(it), *bl = bh + B_TILE;
+                constexpr int GROUPS = BN * 8 / 128;                // (row, 16-byte chunk) groups per thread
+                uint4 hv[GROUPS], lv[GROUPS];
+#pragma unroll
+                for (int u = 0; u < GROUPS; u++) {
+                    const int gi = u * 128 + ct, r = gi >> 3, c = gi & 7;
+                    const float4 f0 = *reinterpret_cast<const float4 *>(rw + (size_t)r * 256 + c * 32);
+                    const float4 f1 = *reinterpret_cast<const float4 *>(rw + (size_t)r * 256 + c * 32 + 16);
+                    const float x[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        // hi = RN(x), lo = RN(x - hi), two elements per (packed) convert
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                        const float2 hf = __bfloat1622float2(h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+                        hh[e] = *reinterpret_cast<const uint32_t *>(&h2);
+                        ll[e] = *reinterpret_cast<const uint32_t *>(&l2);
+                    }
+                    hv[u] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                    lv[u] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty_bar[rs]);     // the fp32 tile is in registers
+                mbar_wait(&bempty_bar[sb], bph ^ 1);                // the MMAs that read this converted-B stage have retired
+#pragma unroll
+                for (int u = 0; u < GROUPS; u++) {
+                    const int gi = u * 128 + ct, r = gi >> 3, c = gi & 7;
+                    const size_t o = (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(bh + o) = hv[u];
+                    *reinterpret_cast<uint4 *>(bl + o) = lv[u];
+                }
+                fence_async_proxy();                                // generic-proxy writes -> tensor-core (async proxy) reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bconv_bar[sb]);
+            }
+        }
+        if (epi_warp) {
+            mbar_wait(&tmem_full_bar, 0);
+            tc_fence_after();
+        }
         if (threadIdx.x == 64) stamp(g, 6);
     }
     pdl_trigger();   // mainloop done on this CTA: the next kernel may be scheduled as SMs drain
@@ -377,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
     if (S > 1) {
         cluster_sync_all();   // every CTA of the cluster has retired its MMAs: stage memory is free everywhere
-        if (warp >= 2) {
+        if (warp >= 2 && warp < 6) {
             for (int p = 0; p < S; p++) {
                 if (p == rank) continue;
                 const uint32_t dst0 = map_to_cta(smem_u32(recv + ((size_t)rank * W4) * TILE_I + row), p);
@@ -393,7 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         cluster_sync_all();   // all partial slabs have landed
     }
     if (threadIdx.x == 64) stamp(g, 7);
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
         for (int c = 0; c < W; c += 16) {
             float v[16];
             tmem_ld16(trow + rank * W + c, v);
@@ -463,14 +561,14 @@ int make_tmap_2d(CUtensorMap *m, const void *base, int dtype_f32, long long rows
     return GGD_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool B_F32 = false>
 static int launch_inst(const GemmPlan &p, cudaStream_t s)
 {
-    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI, B_F32>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.splits, p.tiles_j, p.tiles_i);
-    cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = TileCfg<BN>::SMEM;
+    cfg.blockDim = dim3(B_F32 ? NTHREADS_F32 : NTHREADS);
+    cfg.dynamicSmemBytes = TileCfg<BN, B_F32>::SMEM;
     cfg.stream = s;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -486,6 +584,15 @@ template <int BN>
 static int launch_bn(const GemmPlan &p, cudaStream_t s)
 {
     const int key = p.a_mn * 100 + p.b_mn * 10 + p.epi;
+    if (p.b_f32) {   // B operand = fp32 master weights, split in the kernel
+        switch (key) {
+        case 10 + EPI_FWD_SIGMOID: return launch_inst<BN, false, true, EPI_FWD_SIGMOID, true>(p, s);
+        case 10 + EPI_FWD_LINEAR:  return launch_inst<BN, false, true, EPI_FWD_LINEAR, true>(p, s);
+        case 10 + EPI_FWD_LOSS:    return launch_inst<BN, false, true, EPI_FWD_LOSS, true>(p, s);
+        case 0 + EPI_DX_DSIGMOID:  return launch_inst<BN, false, false, EPI_DX_DSIGMOID, true>(p, s);
+        default: set_error("gemm_tc: no fp32-B variant for a_mn=%d b_mn=%d epi=%d", p.a_mn, p.b_mn, p.epi); return GGD_EINVAL;
+        }
+    }
     switch (key) {
     case 10 + EPI_FWD_SIGMOID: return launch_inst<BN, false, true, EPI_FWD_SIGMOID>(p, s);
     case 10 + EPI_FWD_LINEAR:  return launch_inst<BN, false, true, EPI_FWD_LINEAR>(p, s);
@@ -510,10 +617,10 @@ int launch_gemm_tc(const GemmPlan &p, cudaStream_t s)
     return GGD_EINVAL;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool B_F32 = false>
 static int prep_inst()
 {
-    GGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::SMEM));
+    GGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI, B_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN, B_F32>::SMEM));
     return GGD_OK;
 }
 template <int BN>
@@ -527,6 +634,10 @@ static int prep_bn()
     if ((rc = prep_inst<BN, false, false, EPI_DX_DSIGMOID>())) return rc;
     if ((rc = prep_inst<BN, false, false, EPI_STORE_F32>())) return rc;
     if ((rc = prep_inst<BN, true, true, EPI_STORE_F32>())) return rc;
+    if ((rc = prep_inst<BN, false, true, EPI_FWD_SIGMOID, true>())) return rc;
+    if ((rc = prep_inst<BN, false, true, EPI_FWD_LINEAR, true>())) return rc;
+    if ((rc = prep_inst<BN, false, true, EPI_FWD_LOSS, true>())) return rc;
+    if ((rc = prep_inst<BN, false, false, EPI_DX_DSIGMOID, true>())) return rc;
     return GGD_OK;
 }
 

@@ -41,6 +41,7 @@ struct GemmArgs {
     const bf16 *y_hi, *y_lo;  // EPI_DX_DSIGMOID: activations of the layer whose dE/dx is produced, pitch ldy
     int ldy;
     unsigned long long *trace;   // optional [ctas][16] globaltimer stamps of the pipeline phases (ggd_debug_gemm_timed)
+    unsigned int *hang;          // host-mapped watchdog record (pipe.cuh: mbar_wait_bounded); may be NULL
     // ---- EPI_FWD_LOSS only
     int D;                 // real output units (== J)
     int Mg;                // frames of the GLOBAL minibatch
@@ -60,6 +61,7 @@ struct GemmPlan {
     GemmArgs args;
     int bn;          // 64 or 128
     int a_mn, b_mn;  // operand majors
+    int b_f32;       // B operand is the fp32 master weight matrix (b_hi = fp32 tensor map, box {64, 64 | bn}, no swizzle): split in-kernel
     int epi;
     int splits;      // cluster size along the reduction (1, 2, 4 or 8)
     int tiles_i, tiles_j;
@@ -124,6 +126,7 @@ struct DwpArgs {
     float mom, lr, Mg;
     int advance;                  // last CTA out increments ctl->bunch_idx
     unsigned int *done_counter;
+    int shadows;                  // 1: also write the bf16 hi/lo shadows of the weights (GEMMs in shadow mode, GGD_W_F32=0)
     int l2_hints;                 // evict-first fp32 streams, evict-last shadows (GGD_L2_HINTS, default 1)
     unsigned int *hang;           // host-mapped [8]: filled by a waiter that gave up (see mbar_wait_bounded)
 };

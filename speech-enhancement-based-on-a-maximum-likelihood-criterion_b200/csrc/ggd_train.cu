@@ -92,6 +92,7 @@ struct ggd_handle {
     GemmPlan fwd[GGD_MAXLAYER], dxp[GGD_MAXLAYER], dwp[GGD_MAXLAYER];
     GemmPlan fwd_loss;  // output layer of a training step: the loss-gradient chain runs in its epilogue (EPI_FWD_LOSS)
     bool fuse_loss;
+    bool w_f32;         // GEMMs read the fp32 master weights and split them in-kernel: no bf16 weight shadows are maintained
     DwUpdPlan dwu[GGD_MAXLAYER];
     bool fused;         // gradient GEMM + update fused (single GPU, tensor path)
     bool persist;       // fused AND the bunch is one reduction tile: one persistent launch for all layers (dw_persist.cu)
@@ -196,8 +197,14 @@ static int build_plans(ggd_handle *h)
             p.tiles_i = h->Mp / 128; p.tiles_j = ly.Np / p.bn;
             GGD_TRY(make_tmap_bf16(&p.a_hi, ah, arows, ly.Kp, ly.Kp, 128));
             GGD_TRY(make_tmap_bf16(&p.a_lo, al, arows, ly.Kp, ly.Kp, 128));
-            GGD_TRY(make_tmap_bf16(&p.b_hi, h->Phi + ly.w_off, ly.Kp, ly.Np, ly.Np, 64));
-            GGD_TRY(make_tmap_bf16(&p.b_lo, h->Plo + ly.w_off, ly.Kp, ly.Np, ly.Np, 64));
+            if (h->w_f32) {
+                p.b_f32 = 1;
+                GGD_TRY(make_tmap_2d(&p.b_hi, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 64, 64, 0));
+                p.b_lo = p.b_hi;
+            } else {
+                GGD_TRY(make_tmap_bf16(&p.b_hi, h->Phi + ly.w_off, ly.Kp, ly.Np, ly.Np, 64));
+                GGD_TRY(make_tmap_bf16(&p.b_lo, h->Plo + ly.w_off, ly.Kp, ly.Np, ly.Np, 64));
+            }
             GemmArgs &a = p.args;
             a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
             a.I = h->M; a.J = ly.cur; a.kblocks = ly.Kp / 64;
@@ -215,8 +222,14 @@ static int build_plans(ggd_handle *h)
             p.tiles_i = h->Mp / 128; p.tiles_j = ly.Kp / p.bn;
             GGD_TRY(make_tmap_bf16(&p.a_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 128));
             GGD_TRY(make_tmap_bf16(&p.a_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 128));
-            GGD_TRY(make_tmap_bf16(&p.b_hi, h->Phi + ly.w_off, ly.Kp, ly.Np, ly.Np, p.bn));
-            GGD_TRY(make_tmap_bf16(&p.b_lo, h->Plo + ly.w_off, ly.Kp, ly.Np, ly.Np, p.bn));
+            if (h->w_f32) {
+                p.b_f32 = 1;
+                GGD_TRY(make_tmap_2d(&p.b_hi, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 64, p.bn, 0));
+                p.b_lo = p.b_hi;
+            } else {
+                GGD_TRY(make_tmap_bf16(&p.b_hi, h->Phi + ly.w_off, ly.Kp, ly.Np, ly.Np, p.bn));
+                GGD_TRY(make_tmap_bf16(&p.b_lo, h->Plo + ly.w_off, ly.Kp, ly.Np, ly.Np, p.bn));
+            }
             GemmArgs &a = p.args;
             a.ctl = h->ctl; a.a_rows_from_ctl = 0; a.rows_per_bunch = h->M;
             a.I = h->M; a.J = ly.prev; a.kblocks = ly.Np / 64;
@@ -259,6 +272,7 @@ static int build_plans(ggd_handle *h)
             a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg; a.wc = h->cfg.weightcost;
         }
     }
+    for (int l = 1; l < L; l++) { h->fwd[l].args.hang = h->hang_dev; h->dxp[l].args.hang = h->hang_dev; h->dwp[l].args.hang = h->hang_dev; }
     if (h->fuse_loss) {
         const LayerInfo &top = h->lay[L - 1];
         GemmPlan &p = h->fwd_loss;
@@ -301,7 +315,7 @@ static int build_plans(ggd_handle *h)
         a.total_tiles = base;
         a.ctl = h->ctl; a.rows_per_bunch = h->M; a.M = h->M;
         a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
-        a.advance = 1; a.done_counter = h->dwp_counter; a.hang = h->hang_dev;
+        a.advance = 1; a.done_counter = h->dwp_counter; a.shadows = h->w_f32 ? 0 : 1; a.hang = h->hang_dev;
         { const char *ev = getenv("GGD_L2_HINTS"); a.l2_hints = !(ev && atoi(ev) == 0); }
         GGD_CUDA(cudaMemcpy(h->dwp_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     }
@@ -500,6 +514,7 @@ static int build_dpx(ggd_handle *h)
         for (int p = 0; p < world; p++) {
             if ((rc = make_tmap_2d(&d.hi_map[p], (bf16 *)h->px_peer[4][p] + ly.w_off, 0, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
             if ((rc = make_tmap_2d(&d.lo_map[p], (bf16 *)h->px_peer[5][p] + ly.w_off, 0, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
+            if ((rc = make_tmap_2d(&d.wp_map[p], (float *)h->px_peer[6][p] + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
         }
         d.dx_hi = h->dx_hi[l]; d.dx_lo = h->dx_lo[l];
         d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off;
@@ -523,7 +538,7 @@ static int build_dpx(ggd_handle *h)
     for (int o = 0; o <= world; o++) a->own_begin[o] = h->px_own_begin[o];
     a->total_tiles = h->px_total_tiles; a->world = world; a->rank = rank; a->nbias = (int)h->nbias;
     a->rows_per_bunch = h->M; a->M = h->M;
-    a->k2_stages = h->px_k2_stages; a->k2_stage_bytes = h->px_k2_stage_bytes;
+    a->k2_stages = h->px_k2_stages; a->k2_stage_bytes = h->px_k2_stage_bytes; a->w_f32 = h->w_f32 ? 1 : 0;
     a->mom = h->cfg.momentum; a->lr = h->cfg.lrate; a->Mg = (float)h->Mg;
     cudaError_t e = cudaMemcpy(h->dpx_dev, a, sizeof *a, cudaMemcpyHostToDevice);
     delete a;
@@ -929,6 +944,10 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         const char *ev = getenv("GGD_DW_PERSIST");   // 0: per-layer dw_update launches (tuning / A-B only)
         h->persist = h->fused && h->Mp == 128 && !(ev && atoi(ev) == 0);
     }
+    {
+        const char *ev = getenv("GGD_W_F32");      // 0: bf16 hi/lo weight shadows maintained by the update kernels (first design)
+        h->w_f32 = h->tensor && !(ev && atoi(ev) == 0);
+    }
     const int world = cfg->world_size > 1 ? cfg->world_size : 1;
     h->Mg = h->M * world;
     size_t off = 0;
@@ -1264,7 +1283,7 @@ int ggd_get_weights(ggd_handle *h, float *const *weights, float *const *bias)
     GGD_CUDA(cudaSetDevice(h->cfg.gpu));
     GGD_CUDA(cudaStreamSynchronize(h->s_main));
     if (h->dp_p2p) GGD_TRY(dp_p2p_gather_master(h));
-    if (h->dp_push) {
+    if (h->dp_push && !h->w_f32) {
         // the fp32 master of a tile lives on its owner: pull the foreign tiles (between two cross-rank barriers)
         GGD_TRY(dp_barrier(h));
         launch_gather_master(h->dpx_dev, h->px_peerP_dev, h->px_woff_dev, h->sm_count * 2, h->s_main);

@@ -1,9 +1,32 @@
 """Frame-sharded data parallelism on real GPUs (needs >= 2 devices; `gpurun --gpus 2`): two ranks, each training on
 its shard with NCCL allreduce of sum|e|^beta and of the gradients, must reproduce the unsharded global minibatch."""
 import os
+import queue as _queue
 import sys
+import time
 import numpy as np
 import pytest
+
+
+def _collect(q, ps, timeout):
+    """results of all ranks; fails FAST when a rank process died (a 2-GPU box is charged twice per second waited)"""
+    res, t0 = [], time.time()
+    while len(res) < len(ps):
+        try:
+            res.append(q.get(timeout=2))
+        except _queue.Empty:
+            dead = [p.exitcode for p in ps if p.exitcode not in (None, 0)]
+            if dead:
+                for p in ps:
+                    if p.is_alive():
+                        p.terminate()
+                raise RuntimeError("a rank process died (exit codes %s)" % dead)
+            if time.time() - t0 > timeout:
+                for p in ps:
+                    if p.is_alive():
+                        p.terminate()
+                raise RuntimeError("ranks did not finish within %d s" % timeout)
+    return sorted(res, key=lambda r: r[0])
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -49,7 +72,7 @@ def test_two_gpu_dp_equals_unsharded(pkg, oracle, ml, beta, precision):
     ps = [ctx.Process(target=_rank, args=(r, world, uid, ml, beta, precision, q)) for r in range(world)]
     for p in ps:
         p.start()
-    res = sorted([q.get(timeout=300) for _ in ps], key=lambda r: r[0])
+    res = _collect(q, ps, 240)
     for p in ps:
         p.join(60)
     W, b, x, t = _data(world)
@@ -86,7 +109,7 @@ def test_two_gpu_dp_named_shape(pkg, oracle):
     ps = [ctx.Process(target=_rank, args=(r, world, uid, 1, 1.5, 0, q, NAMED, nb)) for r in range(world)]
     for p in ps:
         p.start()
-    res = sorted([q.get(timeout=600) for _ in ps], key=lambda r: r[0])
+    res = _collect(q, ps, 400)
     for p in ps:
         p.join(60)
     W, b, x, t = _data(world, NAMED, nb)
