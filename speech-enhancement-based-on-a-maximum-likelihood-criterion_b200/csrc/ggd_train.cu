@@ -945,8 +945,12 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         h->persist = h->fused && h->Mp == 128 && !(ev && atoi(ev) == 0);
     }
     {
-        const char *ev = getenv("GGD_W_F32");      // 0: bf16 hi/lo weight shadows maintained by the update kernels (first design)
-        h->w_f32 = h->tensor && !(ev && atoi(ev) == 0);
+        // GGD_W_F32: 1 = GEMMs split the fp32 master weights in-kernel (no shadows; update kernel 57 -> 44 us, GEMMs +1.3 us
+        // each: 124.7 -> 121.9 us per step on one GPU), 0 = bf16 hi/lo shadows maintained by the update kernels.  Default:
+        // on for one GPU; off for data parallelism, where the exchange kernels are NVLink-bound and only the GEMM cost shows
+        // (195 vs 184 us per step at N = 2).
+        const char *ev = getenv("GGD_W_F32");
+        h->w_f32 = h->tensor && (ev ? atoi(ev) != 0 : !(cfg->world_size > 1));
     }
     const int world = cfg->world_size > 1 ? cfg->world_size : 1;
     h->Mg = h->M * world;
