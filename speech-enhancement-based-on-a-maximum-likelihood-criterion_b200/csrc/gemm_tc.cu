@@ -18,9 +18,9 @@ constexpr int BK = 64;                 // reduction elements per stage (128 byte
 constexpr int TILE_I = 128;            // UMMA M
 constexpr int A_TILE = TILE_I * BK * 2;
 constexpr int NTHREADS = 192;           // shadow mode
-constexpr int CONV_GROUPS = 1;           // B_F32: converter groups of 4 warps alternating over the k-blocks (measured: 1 group + a deep
-                                        // raw ring beats 2 groups with separate A / B rings: 123.6 vs 131 us per step)
-constexpr int NTHREADS_F32 = 192 + 128 * (CONV_GROUPS - 1);
+constexpr int CONV_WARPS = 4;            // B_F32: warps that convert every weight tile together (4 = the epilogue warps; 8 measured no faster:
+                                        // the barrier round trips TMA -> convert -> MMA, not the arithmetic, set the latency of a k-block)
+constexpr int NTHREADS_F32 = 64 + 32 * CONV_WARPS;
 
 // B_F32: the B operand (the weight matrix) is read as fp32 straight from the MASTER weights and split into bf16 hi/lo
 // inside the kernel by the epilogue warps (idle during the main loop): no bf16 shadow copy of the weights has to be
@@ -286,8 +286,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < A_ST; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            for (int s = 0; s < B_ST; s++) { mbar_init(&bconv_bar[s], 4); mbar_init(&bempty_bar[s], 1); }
-            for (int s = 0; s < RAW_STAGES; s++) { mbar_init(&raw_full_bar[s], 1); mbar_init(&raw_empty_bar[s], 4 * CONV_GROUPS); }
+            for (int s = 0; s < B_ST; s++) { mbar_init(&bconv_bar[s], B_F32 ? CONV_WARPS : 4); mbar_init(&bempty_bar[s], 1); }
+            for (int s = 0; s < RAW_STAGES; s++) { mbar_init(&raw_full_bar[s], 1); mbar_init(&raw_empty_bar[s], B_F32 ? CONV_WARPS : 4); }
             mbar_init(&tmem_full_bar, 1);
             fence_mbar_init();
         }
@@ -300,14 +300,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const uint32_t tmem = tmem_base_s;
     float loss_tg[16], loss_bs[16];   // EPI_FWD_LOSS: prefetched targets / biases (dead code otherwise)
     int loss_bunch = 0;
-    // everything above overlapped the tail of the previous kernel (PDL); from here on we read what it produced
-    pdl_wait();
-    const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
-    if (threadIdx.x == 0) stamp(g, 1);
+    // Everything above overlapped the tail of the previous kernel (PDL).  Each role waits for the previous grid
+    // (griddepcontrol.wait) right before it first touches what that grid produced -- and not earlier: with B_F32 the weight
+    // tiles do not depend on the previous kernel of the chain (g.b_early), so their TMA loads and their conversion start
+    // while the previous kernel is still draining.
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
+            int early = 0;
+            if constexpr (B_F32) {
+                if (g.b_early) {
+                    early = nkb < RAW_STAGES ? nkb : RAW_STAGES;
+                    for (int it = 0; it < early; it++) {
+                        const int r0 = (kb0 + it) * BK;
+                        mbar_expect_tx(&raw_full_bar[it], RAW_TILE);
+                        uint8_t *rw = raw_ring + it * RAW_TILE;
+                        if constexpr (!B_MN) {
+                            tma_load_2d(rw, &tm_b_hi, &raw_full_bar[it], r0, j0);
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < BN / 64; h++) tma_load_2d(rw + h * 16384, &tm_b_hi, &raw_full_bar[it], j0 + 64 * h, r0);
+                        }
+                    }
+                }
+            }
+            pdl_wait();
+            const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
+            stamp(g, 1);
             for (int it = 0; it < nkb; it++) {
                 const int s = it % A_ST, ph = (it / A_ST) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
@@ -327,6 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 uint8_t *sb = b_stage(it);
                 if constexpr (B_F32) {
                     // fp32 weight tile [BN rows][64 floats] (tm_b_hi is the fp32 map of the master weights)
+                    if (it < early) { if (it == 0) stamp(g, 2); continue; }
                     const int rs = it % RAW_STAGES, rph = (it / RAW_STAGES) & 1;
                     mbar_wait(&raw_empty_bar[rs], rph ^ 1);
                     mbar_expect_tx(&raw_full_bar[rs], RAW_TILE);
@@ -387,7 +408,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     } else {
         // ===== epilogue warps (2..5; with B_F32 also converter group 0) and converter group 1 (warps 6..9, B_F32 only) =====
         const bool epi_warp = warp < 6;
+        if constexpr (!B_F32) pdl_wait();
         if constexpr (EPI == EPI_FWD_LOSS) if (epi_warp) {
+            pdl_wait();
             // targets and biases of this thread's row / first 16-column chunk: requested now, used after the main loop
             const int qq = warp & 3, ii = i0 + qq * 32 + lane, jj = j0 + rank * (BN / S);
             loss_bunch = g.ctl->bunch_idx;
@@ -402,29 +425,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if constexpr (B_F32) {
             // ===== weight converter: fp32 tile -> bf16 hi / lo tiles in the SWIZZLE_128B layout the MMA descriptors expect
             // (row r of 128 bytes, 16-byte chunk c stored at chunk position c ^ (r & 7)) =====
-            // group 0 (warps 2..5) converts the even k-blocks into B stage 0, group 1 (warps 6..9) the odd ones into stage 1:
-            // one conversion (~0.5 us with its barrier round trips) per k-block was the bottleneck of the operand stream
-            static_assert(CONV_GROUPS == 1 || B_ST == 2, "two converter groups <-> two converted-B stages");
-            const int grp = epi_warp ? 0 : 1;
-            const int ct = (threadIdx.x - 64) & 127;               // 0..127 within the group
+            constexpr int CT = 32 * CONV_WARPS;
+            const int ct = threadIdx.x - 64;                       // 0..CT-1
             for (int it = 0; it < nkb; it++) {
                 const int sb = it % B_ST, bph = (it / B_ST) & 1;
                 const int rs = it % RAW_STAGES, rph = (it / RAW_STAGES) & 1;
-                // BOTH groups follow EVERY raw stage (full -> empty) although only one converts it: a group that skipped
-                // the other group's fills could be two phases away from a barrier, which a parity wait cannot detect
                 mbar_wait(&raw_full_bar[rs], rph);
-                if (CONV_GROUPS > 1 && (it % CONV_GROUPS) != grp) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&raw_empty_bar[rs]);
-                    continue;
-                }
                 const uint8_t *rw = raw_ring + rs * RAW_TILE;
                 uint8_t *bh = b_stage(it), *bl = bh + B_TILE;
-                constexpr int GROUPS = BN * 8 / 128;                // (row, 16-byte chunk) groups per thread
+                constexpr int GROUPS = BN * 8 / CT;                 // (row, 16-byte chunk) groups per thread
                 uint4 hv[GROUPS], lv[GROUPS];
 #pragma unroll
                 for (int u = 0; u < GROUPS; u++) {
-                    const int gi = u * 128 + ct, r = gi >> 3, c = gi & 7;
+                    const int gi = u * CT + ct, r = gi >> 3, c = gi & 7;
                     const float4 f0 = *reinterpret_cast<const float4 *>(rw + (size_t)r * 256 + c * 32);
                     const float4 f1 = *reinterpret_cast<const float4 *>(rw + (size_t)r * 256 + c * 32 + 16);
                     const float x[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
@@ -446,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 mbar_wait(&bempty_bar[sb], bph ^ 1);                // the MMAs that read this converted-B stage have retired
 #pragma unroll
                 for (int u = 0; u < GROUPS; u++) {
-                    const int gi = u * 128 + ct, r = gi >> 3, c = gi & 7;
+                    const int gi = u * CT + ct, r = gi >> 3, c = gi & 7;
                     const size_t o = (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4);
                     *reinterpret_cast<uint4 *>(bh + o) = hv[u];
                     *reinterpret_cast<uint4 *>(bl + o) = lv[u];
@@ -456,6 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 if (lane == 0) mbar_arrive(&bconv_bar[sb]);
             }
         }
+        if constexpr (B_F32) pdl_wait();   // (returns at once by now) before the epilogue reads / writes global memory
         if (epi_warp) {
             mbar_wait(&tmem_full_bar, 0);
             tc_fence_after();

@@ -42,6 +42,8 @@ struct GemmArgs {
     int ldy;
     unsigned long long *trace;   // optional [ctas][16] globaltimer stamps of the pipeline phases (ggd_debug_gemm_timed)
     unsigned int *hang;          // host-mapped watchdog record (pipe.cuh: mbar_wait_bounded); may be NULL
+    int b_early;                 // B_F32: the weight tiles may be loaded before griddepcontrol.wait (they were not written by the
+                                 // kernel launched just before this one)
     // ---- EPI_FWD_LOSS only
     int D;                 // real output units (== J)
     int Mg;                // frames of the GLOBAL minibatch

@@ -272,7 +272,11 @@ static int build_plans(ggd_handle *h)
             a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg; a.wc = h->cfg.weightcost;
         }
     }
-    for (int l = 1; l < L; l++) { h->fwd[l].args.hang = h->hang_dev; h->dxp[l].args.hang = h->hang_dev; h->dwp[l].args.hang = h->hang_dev; }
+    for (int l = 1; l < L; l++) {
+        h->fwd[l].args.hang = h->hang_dev; h->dxp[l].args.hang = h->hang_dev; h->dwp[l].args.hang = h->hang_dev;
+        // the weights are written by the update kernel(s) at the END of a step; only the first forward launch follows them directly
+        h->fwd[l].args.b_early = (l != 1); h->dxp[l].args.b_early = 1;
+    }
     if (h->fuse_loss) {
         const LayerInfo &top = h->lay[L - 1];
         GemmPlan &p = h->fwd_loss;
