@@ -325,13 +325,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     }
                 }
             }
+            if constexpr (!B_F32) {
+                // shadow mode: the bf16 weight tiles go straight into the operand stages; their bytes are announced without
+                // the arrival, which follows with the activation tiles after griddepcontrol.wait
+                if (g.b_early) {
+                    early = nkb < A_ST ? nkb : A_ST;
+                    for (int it = 0; it < early; it++) {
+                        const int r0 = (kb0 + it) * BK;
+                        mbar_expect_tx_only(&full_bar[it], 2 * B_TILE);
+                        uint8_t *sb = b_stage(it);
+                        if constexpr (!B_MN) {
+                            tma_load_2d(sb, &tm_b_hi, &full_bar[it], r0, j0);
+                            tma_load_2d(sb + B_TILE, &tm_b_lo, &full_bar[it], r0, j0);
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < BN / 64; h++) {
+                                tma_load_2d(sb + h * 8192, &tm_b_hi, &full_bar[it], j0 + 64 * h, r0);
+                                tma_load_2d(sb + B_TILE + h * 8192, &tm_b_lo, &full_bar[it], j0 + 64 * h, r0);
+                            }
+                        }
+                    }
+                }
+            }
             pdl_wait();
             const int a_row_off = g.a_rows_from_ctl ? g.ctl->bunch_idx * g.rows_per_bunch : 0;
             stamp(g, 1);
             for (int it = 0; it < nkb; it++) {
                 const int s = it % A_ST, ph = (it / A_ST) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], B_F32 ? 2 * A_TILE : STAGE);
+                mbar_expect_tx(&full_bar[s], (B_F32 || it < early) ? 2 * A_TILE : STAGE);
                 uint8_t *st = a_stage(it);
                 const int r0 = (kb0 + it) * BK;
                 if constexpr (!A_MN) {
@@ -358,6 +380,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
                         for (int h = 0; h < BN / 64; h++) tma_load_2d(rw + h * 16384, &tm_b_hi, &raw_full_bar[rs], j0 + 64 * h, r0);
                     }
+                } else if (it < early) {
+                    // already requested before griddepcontrol.wait
                 } else if constexpr (!B_MN) {
                     tma_load_2d(sb, &tm_b_hi, &full_bar[s], r0, j0);
                     tma_load_2d(sb + B_TILE, &tm_b_lo, &full_bar[s], r0, j0);
