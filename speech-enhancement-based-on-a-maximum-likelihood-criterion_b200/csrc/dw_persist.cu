@@ -17,14 +17,15 @@
 //               MMAs of tile t+1 run under the update of tile t;
 //   warps 2..9  update warps: every warp takes part in every ring stage (8 rows x 32 n each): gradient from TMEM,
 //               W / delta from shared memory, delta <- mom*delta - lr*(g/Mg + wc*W), W <- W + delta written back IN
-//               PLACE, bf16 hi/lo shadows into the stage's shadow buffers;
-//   warp 10     store warp: one TMA store per array and stage (W, delta, hi, lo), and it releases the stage to the
+//               PLACE (and, in shadow mode only, the bf16 hi/lo shadows into the stage's shadow buffers);
+//   warp 10     store warp: one TMA store per array and stage (W, delta [, hi, lo]), and it releases the stage to the
 //               producer once the store engine has read it;
 //   warp 11     bias warp: column sums of dx over the frames and the bias update for the n-tiles whose k-tile 0 belongs
 //               to this CTA (latency-bound L2 reads, hidden beside the tile pipeline).
 // Every consumer follows every ring stage in order: a parity wait cannot tell phase f from phase f+2, so no warp may
 // ever skip a stage (TMA loads land out of order).
-// HBM traffic: 16 B/param (+4 B/param of bf16 shadows).  The last CTA to finish advances the device-side bunch counter.
+// HBM traffic: 16 B/param (shadow mode: +4 B/param of bf16 shadows; by default the GEMMs read the fp32 weights and split them
+// in-kernel, gemm_tc.cu B_F32).  The last CTA to finish advances the device-side bunch counter.
 #include "gemm_tc.cuh"
 #include "pipe.cuh"
 #include "../../include/ggd_train.h"
