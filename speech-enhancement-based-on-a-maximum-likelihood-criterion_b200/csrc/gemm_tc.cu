@@ -18,8 +18,10 @@ constexpr int BK = 64;                 // reduction elements per stage (128 byte
 constexpr int TILE_I = 128;            // UMMA M
 constexpr int A_TILE = TILE_I * BK * 2;
 constexpr int NTHREADS = 192;           // shadow mode
-constexpr int CONV_WARPS = 4;            // B_F32: warps that convert every weight tile together (4 = the epilogue warps; 8 measured no faster:
-                                        // the barrier round trips TMA -> convert -> MMA, not the arithmetic, set the latency of a k-block)
+constexpr int CONV_WARPS = 4;            // B_F32: warps that convert every weight tile together (4 = the epilogue warps).  Measured alternatives,
+                                        // all slower or equal (118.2 us per step with this setting): 8 warps on every tile 118.3; two groups of 4
+                                        // alternating over the k-blocks with separate A(3)/B(4)/raw(2) rings 120.5 -- the operand stream is bound by
+                                        // the bytes TMA keeps in flight (3 operand stages + 4 raw stages here), not by the conversion arithmetic
 constexpr int NTHREADS_F32 = 64 + 32 * CONV_WARPS;
 
 // B_F32: the B operand (the weight matrix) is read as fp32 straight from the MASTER weights and split into bf16 hi/lo
