@@ -338,8 +338,15 @@ def main():
             roofs[k] = {"bound": "tensor", "kernel": "gemm_tc_kernel (%s, %d launches/step)" % (k, e["launches_per_step"]), "achieved": e["tflops"],
                         "peak": peaks["bf16_sus"], "unit": "TFLOP/s", "frac": e["tflops"] / peaks["bf16_sus"], "traffic": None,
                         "peak_source": peaks["src"] + " bf16 sustained; algorithmic FLOPs (the pipe executes 3x: bf16x3)",
+                        "traffic_source": None,
                         "note": "128-frame GEMMs are bound by the weight stream, not the tensor pipe: 2*128 FLOP per 4-byte weight = 64 FLOP/B against "
                                 "a machine balance of ~210 FLOP/B; see gemm_tensor_probe for the same kernel at tensor-bound sizes"}
+            gp = os.path.join(ROOT, "profiles", "r01h_gemm_traffic.json")
+            if k == "fwd_gemm" and os.path.exists(gp) and ls == [1799, 2048, 2048, 2048, 257]:
+                gj = json.load(open(gp))
+                roofs[k]["traffic"] = gj["traffic_bytes_per_launch"]          # DRAM bytes of one 128x2048x2048 launch (ncu --set full)
+                roofs[k]["traffic_source"] = gj["source"]
+                roofs[k]["l2_to_sm_bytes_per_launch"] = gj["l2_to_sm_bytes"]
         elif "gbs" in e and k in ("dw_update", "update"):
             roofs[k] = {"bound": "hbm", "kernel": k, "achieved": e["gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": e["gbs"] / peaks["hbm"],
                         "traffic": None, "peak_source": peaks["src"]}
