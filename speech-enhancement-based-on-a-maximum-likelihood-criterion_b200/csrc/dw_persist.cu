@@ -44,10 +44,13 @@ constexpr int WD_ROWS = 16;                        // k rows per ring stage (a q
 constexpr int QUARTERS = TK / WD_ROWS;             // 4
 constexpr int WD_F32 = WD_ROWS * TN * 4;           // 8 KB: 16 k x 128 n fp32
 constexpr int WD_B16 = WD_ROWS * TN * 2;           // 4 KB
-constexpr int WD_STAGE = 2 * WD_F32 + 2 * WD_B16;  // W, delta, hi, lo = 24 KB
 constexpr int WD_LOAD = 2 * WD_F32;                // bytes that arrive by TMA per stage
-constexpr int WD_STAGES = 5;
-constexpr int SMEM = A_SLOT + B_STAGE + WD_STAGES * WD_STAGE + 1024;
+// shadow mode: a stage also stages the bf16 hi/lo tiles (24 KB, 5 stages); without shadows 16 KB, 7 stages
+template <bool SHADOWS> struct Ring {
+    static constexpr int STAGE = 2 * WD_F32 + (SHADOWS ? 2 * WD_B16 : 0);
+    static constexpr int STAGES = SHADOWS ? 5 : 7;
+    static constexpr int SMEM = A_SLOT + B_STAGE + STAGES * STAGE + 1024;
+};
 constexpr int NTHREADS = 384;
 constexpr int TMEM_COLS = 2 * TK;                  // double-buffered accumulator
 }  // namespace dwp
@@ -71,9 +74,11 @@ __device__ __forceinline__ TileRef decode_tile(const DwpArgs *gp, int t)
     return tr;
 }
 
+template <bool SHADOWS>
 __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpArgs *__restrict__ gp)
 {
     using namespace dwp;
+    constexpr int WD_STAGE = Ring<SHADOWS>::STAGE, WD_STAGES = Ring<SHADOWS>::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *a_slot = smem, *b_stage = smem + A_SLOT, *wd_ring = b_stage + B_STAGE;
@@ -206,16 +211,16 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
                     const int c0 = tr.nt * TN, c1 = tr.kt * TK + qt * WD_ROWS;
                     if (gp->l2_hints) {
                         // without shadows the fp32 weights themselves are what the next step's GEMMs read: keep them in L2
-                        tma_store_2d_hint(&L->w_map, src, c0, c1, gp->shadows ? pol_stream : pol_keep);
+                        tma_store_2d_hint(&L->w_map, src, c0, c1, SHADOWS ? pol_stream : pol_keep);
                         tma_store_2d_hint(&L->d_map, src + WD_F32, c0, c1, pol_stream);
-                        if (gp->shadows) {
+                        if (SHADOWS) {
                             tma_store_2d_hint(&L->hi_map, src + 2 * WD_F32, c0, c1, pol_keep);
                             tma_store_2d_hint(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1, pol_keep);
                         }
                     } else {
                         tma_store_2d(&L->w_map, src, c0, c1);
                         tma_store_2d(&L->d_map, src + WD_F32, c0, c1);
-                        if (gp->shadows) {
+                        if (SHADOWS) {
                             tma_store_2d(&L->hi_map, src + 2 * WD_F32, c0, c1);
                             tma_store_2d(&L->lo_map, src + 2 * WD_F32 + WD_B16, c0, c1);
                         }
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
         // ===== update warps (8): quadrant q = accumulator lanes [32q, 32q+32); `h` = which 8 of a stage's 16 rows =====
         const int e = warp - 2, q = warp & 3, h = e >> 2;
         const float mom = gp->mom, lr = gp->lr, inv_mg = 1.0f / gp->Mg;
-        const bool shadows = gp->shadows != 0;
+        constexpr bool shadows = SHADOWS;
         TileRef tr = decode_tile(gp, t0);
         for (int t = t0, it = 0; t < t1; t++, it++) {
             const DwpLayer *L = tr.L;
@@ -344,24 +349,26 @@ __global__ void __launch_bounds__(dwp::NTHREADS, 1) dw_persist_kernel(const DwpA
     }
 }
 
-int launch_dw_persist(const DwpArgs *dev_args, int grid, cudaStream_t s)
+int launch_dw_persist(const DwpArgs *dev_args, int grid, int shadows, cudaStream_t s)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(dwp::NTHREADS);
-    cfg.dynamicSmemBytes = dwp::SMEM;
+    cfg.dynamicSmemBytes = shadows ? dwp::Ring<true>::SMEM : dwp::Ring<false>::SMEM;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    GGD_CUDA(cudaLaunchKernelEx(&cfg, dw_persist_kernel, dev_args));
+    if (shadows) GGD_CUDA(cudaLaunchKernelEx(&cfg, dw_persist_kernel<true>, dev_args));
+    else GGD_CUDA(cudaLaunchKernelEx(&cfg, dw_persist_kernel<false>, dev_args));
     return GGD_OK;
 }
 
 int dw_persist_init()
 {
-    GGD_CUDA(cudaFuncSetAttribute(dw_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwp::SMEM));
+    GGD_CUDA(cudaFuncSetAttribute(dw_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dwp::Ring<true>::SMEM));
+    GGD_CUDA(cudaFuncSetAttribute(dw_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dwp::Ring<false>::SMEM));
     return GGD_OK;
 }
 

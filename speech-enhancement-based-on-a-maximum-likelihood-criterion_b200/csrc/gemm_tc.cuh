@@ -132,7 +132,7 @@ struct DwpArgs {
     int l2_hints;                 // evict-first fp32 streams, evict-last shadows (GGD_L2_HINTS, default 1)
     unsigned int *hang;           // host-mapped [8]: filled by a waiter that gave up (see mbar_wait_bounded)
 };
-int launch_dw_persist(const DwpArgs *dev_args, int grid, cudaStream_t s);
+int launch_dw_persist(const DwpArgs *dev_args, int grid, int shadows, cudaStream_t s);
 int dw_persist_init();
 int gemm_tc_init();   // resolves the driver entry point, sets the shared-memory attributes
 

@@ -653,7 +653,7 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     if (fused && h->persist) {
         // weight gradients + updates of all layers, bias gradients + updates and the bunch counter: one launch
         ProfScope ps(h, KC_DWUPD, s);
-        GGD_TRY(launch_dw_persist(h->dwp_dev, h->sm_count, s)); (*launches)++;
+        GGD_TRY(launch_dw_persist(h->dwp_dev, h->sm_count, h->w_f32 ? 0 : 1, s)); (*launches)++;
         GGD_CUDA(cudaGetLastError());
         return GGD_OK;
     }
