@@ -48,7 +48,7 @@ constexpr int WD_LOAD = 2 * WD_F32;                // bytes that arrive by TMA p
 // shadow mode: a stage also stages the bf16 hi/lo tiles (24 KB, 5 stages); without shadows 16 KB, 7 stages
 template <bool SHADOWS> struct Ring {
     static constexpr int STAGE = 2 * WD_F32 + (SHADOWS ? 2 * WD_B16 : 0);
-    static constexpr int STAGES = SHADOWS ? 5 : 7;
+    static constexpr int STAGES = SHADOWS ? 5 : 8;
     static constexpr int SMEM = A_SLOT + B_STAGE + STAGES * STAGE + 1024;
 };
 constexpr int NTHREADS = 384;
