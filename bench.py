@@ -282,13 +282,14 @@ def main():
     # ---- e2e: the public call with HOST (pinned) buffers: H2D of the chunk + steps + D2H of the loss trace
     e2e = None
     if not args.no_e2e:
-        h_in = torch.randn(nfr, ls[0], generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
-        h_tg = torch.randn(nfr, ls[-1], generator=torch.Generator().manual_seed(8 + rank)).pin_memory()
+        nho = max(nfr, Wm * bunch)
+        h_in = torch.randn(nho, ls[0], generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+        h_tg = torch.randn(nho, ls[-1], generator=torch.Generator().manual_seed(8 + rank)).pin_memory()
         xin, xtg = h_in.numpy(), h_tg.numpy()
         net.train(Wm * bunch, xin[:Wm * bunch], xtg[:Wm * bunch])
         barrier()
         t0 = time.perf_counter()
-        net.train(nfr, xin, xtg)
+        net.train(nfr, xin[:nfr], xtg[:nfr])
         _ = net.losses()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -303,7 +304,8 @@ def main():
 
     # ---- per-kernel times (CUDA events around every launch, no graph) -> roofline of the dominant kernel
     peaks = measured_peaks()
-    kt = net.profile_kernels(64 * bunch, d_in.data_ptr(), d_tg.data_ptr())
+    n_prof = min(64, d_in.shape[0] // bunch)          # bunches available in the resident chunk (small --steps)
+    kt = net.profile_kernels(n_prof * bunch, d_in.data_ptr(), d_tg.data_ptr())
     steps_p = kt["steps"]
     per_step = {k: (kt[k]["ms"] / steps_p, kt[k]["launches"] // max(steps_p, 1)) for k in kt if isinstance(kt[k], dict)}
     fpf = flops_per_frame(ls)
@@ -384,19 +386,20 @@ def main():
         try:
             from oracle import refcuda
             if refcuda.available("libref_bpgpu.so"):
-                nref = 200 * bunch
+                nrb = min(200, d_in.shape[0] // bunch)
+                nref = nrb * bunch
                 xr = d_in[:nref].cpu().numpy(); tr = d_tg[:nref].cpu().numpy()
                 with quiet_stdout():
                     ref = refcuda.RefBPGPU(ls, bunch, LR, MOM, WC, beta, ml, W, b, gpu=local_rank)
-                    ref.train(xr[:8 * bunch], tr[:8 * bunch])
+                    ref.train(xr[:min(8, nrb) * bunch], tr[:min(8, nrb) * bunch])
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     ref.train(xr, tr)
                     torch.cuda.synchronize()
                     dtr = time.perf_counter() - t0
                     ref.close()
-                ref_cuda = {"value": nref / dtr, "unit": "frames/s", "ms_per_step": 1e3 * dtr / 200,
-                            "what": "reference BP_GPU::train (fp32 cuBLAS SGEMM, 53 launches/bunch), 200 bunches incl. its H2D copy"}
+                ref_cuda = {"value": nref / dtr, "unit": "frames/s", "ms_per_step": 1e3 * dtr / nrb,
+                            "what": "reference BP_GPU::train (fp32 cuBLAS SGEMM, 53 launches/bunch), %d bunches incl. its H2D copy" % nrb}
         except Exception as ex:     # the baseline is optional; never let it break the measurement
             ref_cuda = {"unavailable": str(ex)[:200]}
 
