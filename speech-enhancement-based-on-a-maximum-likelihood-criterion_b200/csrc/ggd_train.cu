@@ -818,7 +818,7 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
                      const float *host_targ = nullptr, bool presplit = false)
 {
     const int nb = n_frames / h->M;   // trailing partial bunch dropped (BP_GPU.cu:173-180)
-    const int PIECE = 64;             // bunches per upload piece (a multiple of the 16-step graph)
+    const int PIECE = 16;             // bunches per upload piece (= the 16-step graph): 17 MB, 0.7 ms of PCIe under 1.8 ms of steps
     const bool piped = host_in != nullptr;
     const int D_ = h->units[h->L - 1];
     h->stats.steps = nb; h->stats.launches = 0;
