@@ -324,7 +324,15 @@ def main():
             ent["gbs"] = 16.0 * Ppad / (msk * 1e-3) / 1e9
             ent["tflops"] = gemm_flops["dw_gemm"] / (msk * 1e-3) / 1e12
         if k == "update":
-            ent["gbs"] = 20.0 * kt["param_elems"] / (msk * 1e-3) / 1e9     # read W, delta, g; write W, delta (+4 B shadows not counted)
+            if world > 1:
+                # push-model owner update (reduce_update_kernel): each rank updates 1/world of the parameters: read W, delta and `world`
+                # partial gradient tiles, write W, delta and the local copy of the shadows; the NVLink bytes are not HBM bytes of this rank
+                ent["gbs"] = (16.0 + 4.0 * world + 4.0) * kt["param_elems"] / world / (msk * 1e-3) / 1e9
+                ent["nvlink_gbs_out"] = 4.0 * kt["param_elems"] * (world - 1) / world / (msk * 1e-3) / 1e9
+            else:
+                ent["gbs"] = 20.0 * kt["param_elems"] / (msk * 1e-3) / 1e9     # read W, delta, g; write W, delta (+4 B shadows not counted)
+        if k == "dw_gemm" and world > 1:
+            ent["nvlink_gbs_out"] = 4.0 * kt["param_elems"] * (world - 1) / world / (msk * 1e-3) / 1e9   # gradient tiles pushed to their owners
         if k == "loss":
             ent["gbs"] = (3 * 4 * bunch * 257 + 1028) / (msk * 1e-3) / 1e9
         kern[k] = ent
