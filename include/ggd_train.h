@@ -69,11 +69,12 @@ typedef struct ggd_config {
 
 enum {
     GGD_FLAG_UNFUSED_UPDATE = 1,  /* materialise the weight gradient and run the stand-alone update kernel instead of the
-                                     fused gradient+update kernel (always the case when world_size > 1) */
+                                     fused gradient+update kernel (validation / debugging: the gradient stays readable) */
     GGD_FLAG_NO_GRAPH = 2,        /* launch kernels directly instead of replaying a CUDA graph */
     GGD_FLAG_KEEP_DEBUG = 4,      /* keep per-step tensors readable through ggd_debug_read */
     GGD_FLAG_PIN_HOST = 8         /* cudaHostRegister the caller's (long-lived, reused) chunk buffers on first use;
-                                     the reference's Interface allocates them once (Interface.cc:476-480) */
+                                     the reference's Interface allocates them once (Interface.cc:476-480).  A buffer
+                                     registered this way must stay allocated until ggd_release_host() or ggd_destroy() */
 };
 
 typedef struct ggd_handle ggd_handle;
@@ -107,6 +108,10 @@ typedef struct ggd_raw_chunk {
 } ggd_raw_chunk;
 int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *chunk);
 
+/* Drops the GGD_FLAG_PIN_HOST registration of a host buffer previously passed to ggd_train (call it before freeing or
+ * reallocating such a buffer while the handle lives; unknown pointers are ignored). */
+int ggd_release_host(ggd_handle *h, const void *host_ptr);
+
 /* Same, for a chunk that is already resident in device memory (fp32, same layouts). */
 int ggd_train_device(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ);
 
@@ -136,7 +141,7 @@ int ggd_get_stats(ggd_handle *h, ggd_stats *s);
  * around every launch on the compute stream, and returns the summed milliseconds and launch counts per
  * kernel class (this is what bench.py divides the algorithmic bytes / FLOPs by). */
 enum { GGD_KC_FWD = 0, GGD_KC_LOSS, GGD_KC_DX, GGD_KC_DW, GGD_KC_BIAS, GGD_KC_ALLREDUCE, GGD_KC_UPDATE, GGD_KC_ADVANCE,
-       GGD_KC_SPLIT, GGD_KC_DWUPD, GGD_KC_COUNT };
+       GGD_KC_SPLIT, GGD_KC_DWUPD, GGD_KC_PUSH, GGD_KC_COUNT };
 typedef struct ggd_kernel_times {
     double ms[16];
     long long launches[16];

@@ -11,8 +11,9 @@
  * Pinning: the reference ships NO golden vectors for the training step
  * (SURVEY.md section 4), so this restatement is pinned against the reference's own
  * CUDA binary (oracle/_ref/BPtrain_ref, built from /root/reference by
- * oracle/build_ref.sh) run on a B200: see tests/golden/ref_cuda_*.json and
- * tests/test_oracle_vs_refcuda.py.
+ * oracle/build_ref.sh, and libref_bpgpu.so = BP_GPU.cu + DevFunc.cu behind a C shim) run on
+ * a B200: tests/test_vs_reference_gpu.py; an independent float64 derivation pins the
+ * arithmetic on the CPU (tests/test_oracle_cpu.py).
  *
  * Layout conventions (identical to the reference):
  *   activations  row-major [frame][unit]

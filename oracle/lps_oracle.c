@@ -9,7 +9,7 @@
  *   power + floored ln          Wav2LogSpec_be.c:469-479  (floor exp(-50) -> -50, :54, :303)
  *
  * Pinned bit-exactly against the reference's two golden wav/lps pairs
- * (tests/golden/TEST_DR8_MPAM0_SX{289,379}.{wav,lps}; tests/test_lps_oracle.py) and, in the
+ * (tests/golden/TEST_DR8_MPAM0_SX{289,379}.{wav,lps}; tests/test_oracle_cpu.py) and, in the
  * build container, against the reference binary itself (oracle/_ref/Wav2LPS_be_ref).
  *
  * Arithmetic notes mirrored from the reference: window in double then stored float; twiddles

@@ -34,7 +34,7 @@ class KernelTimes(C.Structure):
     _fields_ = [("ms", C.c_double * 16), ("launches", C.c_longlong * 16), ("steps", C.c_longlong), ("param_elems", C.c_longlong)]
 
 
-KERNEL_CLASSES = ("fwd_gemm", "loss", "dx_gemm", "dw_gemm", "bias_grad", "allreduce", "update", "advance", "split", "dw_update")
+KERNEL_CLASSES = ("fwd_gemm", "loss", "dx_gemm", "dw_gemm", "bias_grad", "allreduce", "update", "advance", "split", "dw_update", "factor_push")
 
 
 def library_path():
@@ -55,6 +55,7 @@ def load_library():
         L.ggd_destroy.argtypes = [C.c_void_p]
         L.ggd_train.argtypes = [C.c_void_p, C.c_int, PF, PF]
         L.ggd_reserve.argtypes = [C.c_void_p, C.c_int]
+        L.ggd_release_host.argtypes = [C.c_void_p, C.c_void_p]
         L.ggd_train_raw.argtypes = [C.c_void_p, C.c_void_p]
         L.ggd_train_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         for f in ("ggd_cv_sqerr", "ggd_cv_abserr", "ggd_cv_loglik"):
@@ -104,6 +105,8 @@ class BP_GPU:
         self.numlayers = int(numlayers)
         self.layersizes = [int(x) for x in layersizes[:numlayers]]
         self.bunchsize = int(bunchsize)
+        self.flags = int(flags)
+        self._long_lived = {}
         if len(weights) == numlayers - 1:
             weights = [None] + list(weights)
             bias = [None] + list(bias)
@@ -148,8 +151,20 @@ class BP_GPU:
 
     # ---- reference surface ---------------------------------------------------------------
     def train(self, n_frames, in_, targ):
-        in_, targ = _f32(in_), _f32(targ)
-        self._ck(self.L.ggd_train(self.h, n_frames, _fp(in_), _fp(targ)))
+        a, t = _f32(in_), _f32(targ)
+        self._ck(self.L.ggd_train(self.h, n_frames, _fp(a), _fp(t)))
+        if self.flags & FLAG_PIN_HOST:
+            # the library registered (pinned) these buffers by address; a temporary made by _f32(), or any array the caller
+            # does not keep for the lifetime of the handle, must not stay registered after it is freed
+            for given, used in ((in_, a), (targ, t)):
+                if used.ctypes.data not in self._long_lived:
+                    self._ck(self.L.ggd_release_host(self.h, C.c_void_p(used.ctypes.data)))
+
+    def keep_pinned(self, *arrays):
+        """Declares host arrays long-lived (the caller keeps them allocated and unchanged in address until close()):
+        with FLAG_PIN_HOST their registration then survives across train() calls, like the reference's chunk buffers."""
+        for a in arrays:
+            self._long_lived[a.ctypes.data] = a
 
     def train_raw(self, fea_records, targ_records, sample_first_frame, fea_dim, fea_context, targ_offset, mean, dvar):
         """Device-side loader (ggd_train_raw): raw big-endian pfile records (uint32 [frames][2+dim]) + the first context

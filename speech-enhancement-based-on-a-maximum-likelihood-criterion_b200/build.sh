@@ -6,12 +6,12 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 -ccbin /usr/bin/g++"
 mkdir -p build
 pids=()
-for f in gemm_tc dw_update dw_persist dp_update dp_push kernels ggd_train lps; do
+for f in gemm_tc dw_persist dw_wide dp_factor kernels ggd_train lps; do
   if [ ! -f build/$f.o ] || [ csrc/$f.cu -nt build/$f.o ] || [ -n "$(find csrc ../include -name '*.h' -newer build/$f.o -o -name '*.cuh' -newer build/$f.o)" ]; then
     $NVCC $FLAGS -c csrc/$f.cu -o build/$f.o &
     pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -cudart shared -ccbin /usr/bin/g++ -o libggd_b200.so build/gemm_tc.o build/dw_update.o build/dw_persist.o build/dp_update.o build/dp_push.o build/kernels.o build/ggd_train.o build/lps.o -lnccl
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -cudart shared -ccbin /usr/bin/g++ -o libggd_b200.so build/gemm_tc.o build/dw_persist.o build/dw_wide.o build/dp_factor.o build/kernels.o build/ggd_train.o build/lps.o -lnccl
 echo "built $(pwd)/libggd_b200.so"

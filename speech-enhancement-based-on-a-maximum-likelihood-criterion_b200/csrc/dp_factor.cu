@@ -1,0 +1,138 @@
+// dp_factor.cu -- see dp_factor.cuh: factor push over NVLink peer memory and the whole-minibatch bias update.
+#include "dp_factor.cuh"
+#include "pipe.cuh"
+#include "../../include/ggd_train.h"
+
+namespace ggd {
+
+__device__ __forceinline__ void st_na_v4(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256) factor_push_kernel(const FxPushArgs a)
+{
+    __shared__ int s_last;
+    const unsigned int step = *a.step_counter + 1u;
+    if (a.wait_done) {
+        // every peer must have finished step-1 (it no longer reads the arena slices this step overwrites)
+        if (threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
+            const unsigned int *f = a.my_flags + threadIdx.x * FX_STRIDE + FX_EV_DONE;
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_sys_u32(f) - (step - 1u)) < 0) {
+                if (clock64() - t0 > (1ll << 33)) {
+                    *a.error_flag = 1u + threadIdx.x;
+                    __threadfence_system();
+                    hang_report(a.hang, 200, (int)step, threadIdx.x);
+                }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+    }
+    const long long bunch = a.ctl->bunch_idx;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int sg = 0; sg < a.nseg; sg++) {
+        const FxSeg S = a.seg[sg];
+        const uint4 *src = reinterpret_cast<const uint4 *>(S.src + S.src_bunch_stride * bunch);
+        const long long n16 = S.bytes >> 4;
+        for (long long i = tid; i < n16; i += 4ll * nth) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long j = i + (long long)u * nth;
+                if (j < n16) v[u] = __ldg(src + j);
+            }
+            for (int p = 0; p < a.world; p++) {
+                if (p == a.rank && !a.include_self) continue;
+                uint4 *dst = reinterpret_cast<uint4 *>(a.peer_arena[p] + S.dst_off);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const long long j = i + (long long)u * nth;
+                    if (j < n16) st_na_v4(dst + j, v[u]);
+                }
+            }
+        }
+    }
+    // flag: once EVERY block's stores are performed system-wide, tell all peers
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(a.block_counter, 1u);
+        s_last = (prev == gridDim.x - 1);
+        if (s_last) {
+            *a.block_counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < a.world; p++)
+                if (p != a.rank) st_release_sys_u32(a.peer_flags[p] + a.rank * FX_STRIDE + a.event, step);
+        }
+    }
+}
+
+void launch_factor_push(const FxPushArgs &a, int grid, cudaStream_t s)
+{
+    factor_push_kernel<<<grid, 256, 0, s>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int BW_COLS = 32, BW_ROWL = 32;
+__global__ void __launch_bounds__(BW_COLS *BW_ROWL) bias_wide_kernel(const BiasWideArgs a)
+{
+    __shared__ float red[BW_ROWL][BW_COLS + 1];
+    const BiasWideLayer L = a.layer[blockIdx.y];
+    const int tx = threadIdx.x % BW_COLS, ty = threadIdx.x / BW_COLS;
+    const int n = blockIdx.x * BW_COLS + tx;
+    const bool active = blockIdx.x * BW_COLS < L.N;
+    if (active && a.world > 1 && L.ev_dx >= 0) {
+        const unsigned int step = *a.bias_step + 1u;
+        if (threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
+            const unsigned int *f = a.flags + threadIdx.x * FX_STRIDE + L.ev_dx;
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_sys_u32(f) - step) < 0) {
+                if (clock64() - t0 > (1ll << 33)) {
+                    *a.error_flag = 1u + threadIdx.x;
+                    __threadfence_system();
+                    hang_report(a.hang, 300 + L.ev_dx, (int)step, threadIdx.x);
+                }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+    }
+    if (active) {
+        float s = 0.0f;
+        if (n < L.N)
+            for (int m = ty; m < a.rows; m += BW_ROWL) s += join_bf16(L.hi[(size_t)m * L.ld + n], L.lo[(size_t)m * L.ld + n]);
+        red[ty][tx] = s;
+        __syncthreads();
+        if (ty == 0 && n < L.N) {
+            float g = red[0][tx];
+#pragma unroll
+            for (int r = 1; r < BW_ROWL; r++) g += red[r][tx];     // fixed order: identical on every rank
+            const float db = a.mom * L.db[n] - a.lr * (g / a.Mg);   // no weight cost on biases (BP_GPU.cu:435)
+            L.db[n] = db;
+            L.b[n] = db + L.b[n];
+        }
+    }
+    // last block out counts the bias step (every block has read the counter above)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int total = gridDim.x * gridDim.y;
+        const unsigned int prev = atomicAdd(a.block_counter, 1u);
+        if (prev == total - 1) {
+            *a.block_counter = 0;
+            *a.bias_step += 1u;
+        }
+    }
+}
+
+void launch_bias_wide(const BiasWideArgs &a, cudaStream_t s)
+{
+    int maxn = 1;
+    for (int l = 0; l < a.nlayers; l++) maxn = a.layer[l].N > maxn ? a.layer[l].N : maxn;
+    dim3 grid(ceil_div(maxn, BW_COLS), a.nlayers);
+    bias_wide_kernel<<<grid, BW_COLS * BW_ROWL, 0, s>>>(a);
+}
+
+}  // namespace ggd

@@ -147,7 +147,7 @@ __device__ __forceinline__ float pow_abs_g(float a, float p)
 // (3 000 instructions in the first version) was bound by instruction fetch -- 11 us instead of 1.
 //   e = out - targ, s_d = sum over the 128 rows (8 row groups, fixed order), alpha_d = (beta*s_d/Mg)^(1/beta),
 //   dE/dx = (1/Mg) sgn(e)|e|^(beta-1) beta [/ alpha_d^beta] as bf16 hi/lo, exactly 0 at e == 0 (DevFunc.cu:388-391, 479-482).
-// With world > 1 the partial s_d are exchanged over peer memory (dp_push.cuh) so that alpha is the unsharded minibatch's.
+// With world > 1 the partial s_d are exchanged over peer memory (dp_factor.cuh) so that alpha is the unsharded minibatch's.
 // `tg` / `bs`: targets and biases of this thread's row and 16 columns, loaded by the caller BEFORE it waits for the accumulator
 // (they do not depend on the GEMM; the epilogue warps are idle during the main loop anyway).
 __device__ __forceinline__ void epilogue_loss16(const GemmArgs &g, int i, int j, float *v, int t, const float *tg, const float *bs, int bunch)
@@ -196,9 +196,9 @@ __device__ __forceinline__ void epilogue_loss16(const GemmArgs &g, int i, int j,
             __syncwarp(0x0000ffffu);
             if (t == 0)
                 for (int pr = 0; pr < g.world; pr++)
-                    if (pr != g.rank) st_release_sys_u32(g.lflags[pr] + g.rank * LOSS_FLAGS_PER_RANK + chunk, step);
+                    if (pr != g.rank) st_release_sys_u32(g.lflags[pr] + g.rank * FX_STRIDE + FX_EV_LOSS + chunk, step);
             if (t < g.world && t != g.rank) {
-                const unsigned int *f = g.lflags[g.rank] + t * LOSS_FLAGS_PER_RANK + chunk;
+                const unsigned int *f = g.lflags[g.rank] + t * FX_STRIDE + FX_EV_LOSS + chunk;
                 const long long t0 = clock64();
                 while ((int)(ld_acquire_sys_u32(f) - step) < 0) {
                     if (clock64() - t0 > (1ll << 32)) { *g.error_flag = 1u + t; break; }
@@ -615,7 +615,7 @@ static int launch_inst(const GemmPlan &p, cudaStream_t s)
     at[0].val.clusterDim.x = p.splits; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
+    cfg.attrs = at; cfg.numAttrs = p.no_pdl ? 1 : 2;
     GGD_CUDA(cudaLaunchKernelEx(&cfg, kern, p.a_hi, p.a_lo, p.b_hi, p.b_lo, p.args));
     return GGD_OK;
 }

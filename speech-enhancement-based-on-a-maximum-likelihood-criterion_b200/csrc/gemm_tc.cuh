@@ -25,7 +25,6 @@ enum GemmEpilogue {
                           // (BP_GPU.cu:408-424) in the epilogue: e = out - targ, s_d = sum_m |e|^beta, alpha_d, dE/dx as bf16 hi/lo
 };
 
-constexpr int LOSS_FLAGS_PER_RANK = 32;   // data-parallel alpha exchange: one flag per source rank and 16-column chunk
 
 struct GemmArgs {
     const StepCtl *ctl;
@@ -51,9 +50,9 @@ struct GemmArgs {
     int ml;                // MLflag == 1
     float *alpha;          // [D]
     double *loss_trace;    // per-bunch loss, indexed by ctl->bunch_idx (may be NULL)
-    int world, rank;       // world > 1: partial column sums are exchanged over peer memory (dp_push.cuh)
+    int world, rank;       // world > 1: partial column sums are exchanged over peer memory (dp_factor.cuh)
     float *asum_slot[8];   // every rank's receive area [world][D]
-    unsigned int *lflags[8];   // every rank's flags [world][LOSS_FLAGS_PER_RANK]
+    unsigned int *lflags[8];   // every rank's flag block [world][FX_STRIDE] (kernels.cuh); the loss flags sit at FX_EV_LOSS
     const unsigned int *step_counter;
     unsigned int *error_flag;
 };
@@ -66,6 +65,7 @@ struct GemmPlan {
     int b_f32;       // B operand is the fp32 master weight matrix (b_hi = fp32 tensor map, box {64, 64 | bn}, no swizzle): split in-kernel
     int epi;
     int splits;      // cluster size along the reduction (1, 2, 4 or 8)
+    int no_pdl;      // launch WITHOUT programmatic stream serialization (first kernel after a cross-stream join)
     int tiles_i, tiles_j;
 };
 
@@ -77,30 +77,6 @@ int make_tmap_2d(CUtensorMap *m, const void *base, int dtype_f32, long long rows
                  int swizzle128);
 
 int launch_gemm_tc(const GemmPlan &p, cudaStream_t s);
-
-// ---- fused gradient GEMM + momentum-SGD update (dw_update.cu) ------------------------------------------------------
-// g[k][n] = sum_m y[m][k] dx[m][n] for one 128 x 64 tile of a weight matrix stays on chip (TMEM -> shared memory) and
-// is consumed at once by  delta <- mom*delta - lr*(g/Mg + wc*W);  W <- W + delta  (kernUpdatedelta + kernAccSum,
-// DevFunc.cu:490-507, 427-443) with coalesced row-wise W / delta traffic: 16 B/param of HBM traffic
-// (+4 B/param for the bf16 hi/lo operand shadows) instead of 28 when the gradient is materialised.
-struct DwUpdArgs {
-    const StepCtl *ctl;
-    int a_rows_from_ctl, rows_per_bunch;
-    int kblocks;              // frames / 64
-    int Kp, Np;
-    float *W, *D;             // fp32 weights and momentum of this layer, pitch Np
-    bf16 *w_hi, *w_lo;        // shadows, pitch Np
-    float mom, lr, Mg, wc;
-    unsigned long long *trace;   // optional [ctas][16] globaltimer stamps
-};
-struct DwUpdPlan {
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;   // operands (bf16, MN-major boxes)
-    DwUpdArgs args;
-    int tiles_i, tiles_j;
-    int stages;                           // operand ring depth: 1 (48 KB, up to 3 CTAs per SM) or 2
-};
-int launch_dw_update(const DwUpdPlan &p, cudaStream_t s);
-int dw_update_init();
 
 // ---- persistent gradient + update kernel for ALL layers and biases in one launch (dw_persist.cu; Mp == 128) ---------
 // The argument block lives in device memory (its tensor maps are read by TMA from there).

@@ -5,13 +5,14 @@
 // Reference behaviour restated (not ported): Train_code_ML_GGD/BP_GPU.cu.  Differences by design:
 //   * 53 launches + 5 host syncs per bunch become one graph replay per 16 bunches;
 //   * cuBLAS fp32 SGEMM becomes the tcgen05 bf16x3 GEMM of gemm_tc.cu (no cuBLAS anywhere);
-//   * the 11-kernel loss chain is one kernel; the 4-launch-per-layer update is one launch per step;
-//   * all weights live in one padded arena so that update / allreduce are single flat passes.
+//   * the 11-kernel loss chain runs in the output-layer GEMM's epilogue; the 4-launch-per-layer update is one launch per step;
+//   * all weights live in one padded arena so that update / allreduce are single flat passes;
+//   * data parallelism exchanges the low-rank FACTORS of the gradient over NVLink peer memory (dp_factor.cuh).
 #include "../../include/ggd_train.h"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
-#include "dp_update.cuh"
-#include "dp_push.cuh"
+#include "dw_wide.cuh"
+#include "dp_factor.cuh"
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -49,6 +50,9 @@ using namespace ggd;
     } while (0)
 
 constexpr int HANG_WORDS = 8 + 160 * 12 * 4;
+constexpr int FX_NEVENTS = 24;      // fork / join events of one step
+// fx_counters words
+constexpr int FXC_STEP = 0, FXC_BIAS_STEP = 1, FXC_BIAS_BLOCKS = 2, FXC_ERROR = 3, FXC_PUSH_BLOCKS = 8, FXC_WORDS = 8 + FX_STRIDE;
 
 struct LayerInfo {
     int prev, cur;      // real units
@@ -67,8 +71,13 @@ struct ggd_handle {
     size_t arena;
     float *P, *Dl, *G;
     bf16 *Phi, *Plo;
-    // per-layer activations / gradients of one bunch
-    bf16 *act_hi[GGD_MAXLAYER], *act_lo[GGD_MAXLAYER], *dx_hi[GGD_MAXLAYER], *dx_lo[GGD_MAXLAYER];
+    // FACTOR ARENA (one allocation, tensor path): per layer the activations and dE/dx of one minibatch as bf16 hi/lo
+    // [fx_rows][upad].  fx_rows = Mp on one GPU; world*Mp with factor-exchange data parallelism, where this rank's GEMMs
+    // read and write the slice of rows [loc_row, loc_row + Mp) and the peers push the other slices (dp_factor.cuh).
+    uint8_t *fx_arena;
+    size_t fx_bytes;
+    int fx_rows, loc_row;
+    bf16 *act_hi[GGD_MAXLAYER], *act_lo[GGD_MAXLAYER], *dx_hi[GGD_MAXLAYER], *dx_lo[GGD_MAXLAYER];   // whole arrays (row 0)
     float *x32[GGD_MAXLAYER], *y32[GGD_MAXLAYER], *dy32[GGD_MAXLAYER], *dx32[GGD_MAXLAYER];
     float *out32;       // [Mp][upad[L-1]]
     float *alpha, *colsum;
@@ -86,39 +95,36 @@ struct ggd_handle {
     std::vector<cudaEvent_t> ev_piece;   // upload pipeline: piece p of the chunk has landed
     cudaEvent_t ev_c0, ev_c1;
     cudaEvent_t ev0, ev1, ev2;
-    cudaEvent_t ev_dw[GGD_MAXLAYER], ev_bias, ev_done;   // fork/join between the compute and the communication stream
+    cudaEvent_t ev_fx[FX_NEVENTS];       // fork / join between the compute stream and the side stream (pushes, bias update)
     size_t nbias;       // packed bias-gradient elements
     // plans + graphs
     GemmPlan fwd[GGD_MAXLAYER], dxp[GGD_MAXLAYER], dwp[GGD_MAXLAYER];
     GemmPlan fwd_loss;  // output layer of a training step: the loss-gradient chain runs in its epilogue (EPI_FWD_LOSS)
     bool fuse_loss;
     bool w_f32;         // GEMMs read the fp32 master weights and split them in-kernel: no bf16 weight shadows are maintained
-    DwUpdPlan dwu[GGD_MAXLAYER];
-    bool fused;         // gradient GEMM + update fused (single GPU, tensor path)
-    bool persist;       // fused AND the bunch is one reduction tile: one persistent launch for all layers (dw_persist.cu)
-    DwpArgs *dwp_dev;   // its argument block (device memory)
+    bool fused;         // gradient GEMM + update fused (tensor path; one GPU or factor-exchange data parallelism)
+    bool persist;       // fused, one GPU, the bunch is one reduction tile: dw_persist.cu
+    bool wide;          // fused, any other case: dw_wide.cu + bias_wide_kernel
+    DwpArgs *dwp_dev;   // argument block of dw_persist (device memory)
+    DwwArgs *dww_dev;   // argument block of dw_wide (device memory)
+    int wide_smem;
+    BiasWideArgs bias_wide;
     unsigned int *dwp_counter;
     unsigned int *hang_host, *hang_dev;   // host-mapped record written by a device-side watchdog before it traps
     cudaGraphExec_t g1, gN;
     int gN_steps;
     int launches_per_step;
-    // DP
+    // data parallelism
     ncclComm_t comm;
     bool has_comm;
-    bool dp_p2p;        // fused reduce-scatter + sharded update + all-gather over NVLink peer memory (dp_update.cu)
-    DpArgs dpa[GGD_MAXLAYER];   // one fused exchange+update launch per layer (index = layer; biases ride with layer 1)
-    void *peer_base[5][DP_MAX_RANKS];   // IPC-mapped peer allocations (G, Phi, Plo, P, flags)
-    unsigned int *dp_flags, *dp_counters;   // local: per layer [2][DP_MAX_RANKS] arrival flags; per layer {step, blocks}, then {error}
-    int dp_overlap;     // 0 (default): one allreduce at the end; 1: per-layer allreduce + update on the communication stream
-    // push-model data parallelism (dp_push.cuh): gradient tiles pushed to their owners, shadows pushed back, no NCCL on the step
-    bool dp_push;
-    DpxArgs *dpx_dev;
-    float *px_rbuf, *px_bias, *px_asum;          // receive slots: gradient tiles, bias partials, sum|e|^beta partials
-    unsigned int *px_flags, *px_counters;         // flags (written by peers), {step, k1_done, k2_done, error}
-    void *px_peer[7][DPX_MAX];                    // IPC-mapped: rbuf, bias, asum, flags, Phi, Plo, P
-    int px_own_begin[DPX_MAX + 1], px_slot_tiles, px_total_tiles, px_k2_smem, px_k2_stages, px_k2_stage_bytes;
-    float **px_peerP_dev; long long *px_woff_dev;
-    unsigned long long *px_trace;
+    bool dp_fx;         // factor exchange over NVLink peer memory (dp_factor.cuh); otherwise NCCL allreduce of the gradient arena
+    bool fx_loss;       // sum|e|^beta exchanged over peer memory inside the loss epilogue / loss_kernel
+    float *fx_asum;                 // receive slots of the sum|e|^beta partials [world][D]
+    unsigned int *fx_flags;         // my flag block [world][FX_STRIDE]
+    unsigned int *fx_counters;      // FXC_*
+    void *fx_peer[3][FX_MAX];       // IPC-mapped: factor arena, asum, flags of every rank
+    FxPushArgs fx_push[FX_STRIDE];  // by event (FX_EV_Y + l, FX_EV_DX + l)
+    int fx_push_ctas;
     // host mirrors / stats
     std::vector<float> losses;
     std::vector<float> h_out;
@@ -129,7 +135,8 @@ struct ggd_handle {
     std::vector<int> prof_cls;
 };
 
-enum { KC_FWD = 0, KC_LOSS, KC_DX, KC_DW, KC_BIAS, KC_ALLREDUCE, KC_UPDATE, KC_ADVANCE, KC_SPLIT, KC_DWUPD, KC_COUNT };
+enum { KC_FWD = 0, KC_LOSS, KC_DX, KC_DW, KC_BIAS, KC_ALLREDUCE, KC_UPDATE, KC_ADVANCE, KC_SPLIT, KC_DWUPD, KC_PUSH, KC_COUNT };
+static_assert((int)KC_COUNT == (int)GGD_KC_COUNT, "kernel classes out of sync with include/ggd_train.h");
 
 struct ProfScope {
     ggd_handle *h; cudaStream_t s;
@@ -143,8 +150,8 @@ struct ProfScope {
     ~ProfScope() { if (h->prof_on) cudaEventRecord(h->prof_ev.back(), s); }
 };
 
-static int dp_p2p_setup(ggd_handle *h);
-static int build_dpx(ggd_handle *h);
+// this rank's slice of a factor array
+static inline bf16 *loc(const ggd_handle *h, bf16 *base, int l) { return base + (size_t)h->loc_row * h->upad[l]; }
 
 static void free_chunk(ggd_handle *h)
 {
@@ -182,11 +189,13 @@ static void pick_tile(int tiles_i, int Np, int kblocks, int sm, int *bn_out, int
 static int build_plans(ggd_handle *h)
 {
     const int L = h->L;
+    const int world = h->dp_fx ? h->cfg.world_size : 1, rank = h->dp_fx ? h->cfg.rank : 0;
     for (int l = 1; l < L; l++) {
         const LayerInfo &ly = h->lay[l];
         const bool first = (l == 1), last = (l == L - 1);
-        const bf16 *ah = first ? h->c_hi : h->act_hi[l - 1], *al = first ? h->c_lo : h->act_lo[l - 1];
+        const bf16 *ah = first ? h->c_hi : loc(h, h->act_hi[l - 1], l - 1), *al = first ? h->c_lo : loc(h, h->act_lo[l - 1], l - 1);
         const long long arows = first ? (long long)h->cap : h->Mp;
+        bf16 *dxh = loc(h, h->dx_hi[l], l), *dxl = loc(h, h->dx_lo[l], l);
         // ---- forward: x[m][n] = sum_k y[m][k] W[k][n]
         {
             GemmPlan &p = h->fwd[l];
@@ -209,7 +218,7 @@ static int build_plans(ggd_handle *h)
             a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
             a.I = h->M; a.J = ly.cur; a.kblocks = ly.Kp / 64;
             a.bias = h->P + ly.b_off;
-            a.o_hi = h->act_hi[l]; a.o_lo = h->act_lo[l]; a.ldo = ly.Np;
+            a.o_hi = loc(h, h->act_hi[l], l); a.o_lo = loc(h, h->act_lo[l], l); a.ldo = ly.Np;
             a.o32 = h->out32; a.ld32 = ly.Np;
         }
         // ---- backward: dE/dy[m][k] = sum_n dE/dx[m][n] W[k][n], times y(1-y) of layer l-1
@@ -220,8 +229,8 @@ static int build_plans(ggd_handle *h)
             p.a_mn = 0; p.b_mn = 0;
             p.epi = EPI_DX_DSIGMOID;
             p.tiles_i = h->Mp / 128; p.tiles_j = ly.Kp / p.bn;
-            GGD_TRY(make_tmap_bf16(&p.a_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 128));
-            GGD_TRY(make_tmap_bf16(&p.a_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 128));
+            GGD_TRY(make_tmap_bf16(&p.a_hi, dxh, h->Mp, ly.Np, ly.Np, 128));
+            GGD_TRY(make_tmap_bf16(&p.a_lo, dxl, h->Mp, ly.Np, ly.Np, 128));
             if (h->w_f32) {
                 p.b_f32 = 1;
                 GGD_TRY(make_tmap_2d(&p.b_hi, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 64, p.bn, 0));
@@ -233,10 +242,10 @@ static int build_plans(ggd_handle *h)
             GemmArgs &a = p.args;
             a.ctl = h->ctl; a.a_rows_from_ctl = 0; a.rows_per_bunch = h->M;
             a.I = h->M; a.J = ly.prev; a.kblocks = ly.Np / 64;
-            a.o_hi = h->dx_hi[l - 1]; a.o_lo = h->dx_lo[l - 1]; a.ldo = ly.Kp;
-            a.y_hi = h->act_hi[l - 1]; a.y_lo = h->act_lo[l - 1]; a.ldy = ly.Kp;
+            a.o_hi = loc(h, h->dx_hi[l - 1], l - 1); a.o_lo = loc(h, h->dx_lo[l - 1], l - 1); a.ldo = ly.Kp;
+            a.y_hi = loc(h, h->act_hi[l - 1], l - 1); a.y_lo = loc(h, h->act_lo[l - 1], l - 1); a.ldy = ly.Kp;
         }
-        // ---- gradient: g[k][n] = sum_m y[m][k] dE/dx[m][n]
+        // ---- gradient of this rank's frames, materialised: g[k][n] = sum_m y[m][k] dE/dx[m][n]  (validation / NCCL mode)
         {
             GemmPlan &p = h->dwp[l];
             memset(&p, 0, sizeof p);
@@ -246,30 +255,13 @@ static int build_plans(ggd_handle *h)
             p.tiles_i = ceil_div(ly.Kp, 128); p.tiles_j = ly.Np / p.bn;
             GGD_TRY(make_tmap_bf16(&p.a_hi, ah, arows, ly.Kp, ly.Kp, 64));
             GGD_TRY(make_tmap_bf16(&p.a_lo, al, arows, ly.Kp, ly.Kp, 64));
-            GGD_TRY(make_tmap_bf16(&p.b_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 64));
-            GGD_TRY(make_tmap_bf16(&p.b_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 64));
+            GGD_TRY(make_tmap_bf16(&p.b_hi, dxh, h->Mp, ly.Np, ly.Np, 64));
+            GGD_TRY(make_tmap_bf16(&p.b_lo, dxl, h->Mp, ly.Np, ly.Np, 64));
             GemmArgs &a = p.args;
             a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
             a.I = ly.Kp; a.J = ly.Np; a.kblocks = h->Mp / 64;
             a.o32 = h->G + ly.w_off; a.ld32 = ly.Np;
             p.splits = 1;
-        }
-        // ---- fused gradient + update
-        {
-            DwUpdPlan &p = h->dwu[l];
-            memset(&p, 0, sizeof p);
-            p.tiles_i = ceil_div(ly.Kp, 128); p.tiles_j = ly.Np / 64;
-            GGD_TRY(make_tmap_bf16(&p.a_hi, ah, arows, ly.Kp, ly.Kp, 64));
-            GGD_TRY(make_tmap_bf16(&p.a_lo, al, arows, ly.Kp, ly.Kp, 64));
-            GGD_TRY(make_tmap_bf16(&p.b_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 64));
-            GGD_TRY(make_tmap_bf16(&p.b_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 64));
-            p.stages = 2;
-            DwUpdArgs &a = p.args;
-            a.ctl = h->ctl; a.a_rows_from_ctl = first; a.rows_per_bunch = h->M;
-            a.kblocks = h->Mp / 64; a.Kp = ly.Kp; a.Np = ly.Np;
-            a.W = h->P + ly.w_off; a.D = h->Dl + ly.w_off;
-            a.w_hi = h->Phi + ly.w_off; a.w_lo = h->Plo + ly.w_off;
-            a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg; a.wc = h->cfg.weightcost;
         }
     }
     for (int l = 1; l < L; l++) {
@@ -277,19 +269,20 @@ static int build_plans(ggd_handle *h)
         // the weights are written by the update kernel(s) at the END of a step; only the first forward launch follows them directly
         h->fwd[l].args.b_early = (l != 1); h->dxp[l].args.b_early = 1;
     }
+    { const char *ev = getenv("GGD_WIDE_PDL"); h->fwd[1].no_pdl = h->wide && !(ev && atoi(ev) == 1); }   // fwd[1] follows the join with the side stream
     if (h->fuse_loss) {
         const LayerInfo &top = h->lay[L - 1];
         GemmPlan &p = h->fwd_loss;
         p = h->fwd[L - 1];
         p.epi = EPI_FWD_LOSS;
         GemmArgs &a = p.args;
-        a.o_hi = h->dx_hi[L - 1]; a.o_lo = h->dx_lo[L - 1]; a.ldo = top.Np;
+        a.o_hi = loc(h, h->dx_hi[L - 1], L - 1); a.o_lo = loc(h, h->dx_lo[L - 1], L - 1); a.ldo = top.Np;
         a.D = top.cur; a.Mg = h->Mg; a.beta = h->cfg.shapefactor; a.ml = (h->cfg.MLflag == 1);
         a.alpha = h->alpha; a.loss_trace = h->trace;
-        a.world = h->dp_push ? h->cfg.world_size : 1; a.rank = h->cfg.rank;
-        if (h->dp_push) {
-            a.step_counter = h->px_counters; a.error_flag = h->px_counters + 4;
-            for (int q = 0; q < a.world; q++) { a.asum_slot[q] = (float *)h->px_peer[2][q]; a.lflags[q] = (unsigned int *)h->px_peer[3][q] + DPX_FLAG_LOSS; }
+        a.world = h->fx_loss ? h->cfg.world_size : 1; a.rank = h->cfg.rank;
+        if (h->fx_loss) {
+            a.step_counter = h->fx_counters + FXC_STEP; a.error_flag = h->fx_counters + FXC_ERROR;
+            for (int q = 0; q < a.world; q++) { a.asum_slot[q] = (float *)h->fx_peer[1][q]; a.lflags[q] = (unsigned int *)h->fx_peer[2][q]; }
         }
     }
     if (h->persist) {
@@ -299,9 +292,12 @@ static int build_plans(ggd_handle *h)
         int base = 0;
         for (int l = 1; l < L; l++) {
             const LayerInfo &ly = h->lay[l];
+            const bool first = (l == 1);
             DwpLayer &d = a.layer[a.nlayers++];
-            d.a_hi = h->dwu[l].b_hi; d.a_lo = h->dwu[l].b_lo;   // dE/dx, box {64, 64}
-            d.b_hi = h->dwu[l].a_hi; d.b_lo = h->dwu[l].a_lo;   // activations below, box {64, 64}
+            GGD_TRY(make_tmap_bf16(&d.a_hi, h->dx_hi[l], h->Mp, ly.Np, ly.Np, 64));      // dE/dx, box {64, 64}
+            GGD_TRY(make_tmap_bf16(&d.a_lo, h->dx_lo[l], h->Mp, ly.Np, ly.Np, 64));
+            GGD_TRY(make_tmap_bf16(&d.b_hi, first ? h->c_hi : h->act_hi[l - 1], first ? (long long)h->cap : h->Mp, ly.Kp, ly.Kp, 64));   // activations below
+            GGD_TRY(make_tmap_bf16(&d.b_lo, first ? h->c_lo : h->act_lo[l - 1], first ? (long long)h->cap : h->Mp, ly.Kp, ly.Kp, 64));
             d.W = h->P + ly.w_off; d.D = h->Dl + ly.w_off; d.w_hi = h->Phi + ly.w_off; d.w_lo = h->Plo + ly.w_off;
             d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off;
             GGD_TRY(make_tmap_2d(&d.w_map, d.W, 1, ly.Kp, ly.Np, ly.Np, 128, 16, 0));
@@ -312,7 +308,7 @@ static int build_plans(ggd_handle *h)
             d.Kp = ly.Kp; d.Np = ly.Np; d.N = ly.cur;
             d.k_tiles = ly.Kp / 64;
             d.tile_base = base;
-            d.b_rows_from_ctl = (l == 1);
+            d.b_rows_from_ctl = first;
             d.wc = h->cfg.weightcost;
             base += ceil_div(ly.Np, 128) * d.k_tiles;
         }
@@ -323,7 +319,76 @@ static int build_plans(ggd_handle *h)
         { const char *ev = getenv("GGD_L2_HINTS"); a.l2_hints = !(ev && atoi(ev) == 0); }
         GGD_CUDA(cudaMemcpy(h->dwp_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     }
-    if (h->dp_push) GGD_TRY(build_dpx(h));
+    if (h->wide) {
+        // slab list over all layers, TOP layer first (in data-parallel mode its factors arrive first)
+        DwwArgs *a = new DwwArgs();
+        memset(a, 0, sizeof *a);
+        int base = 0, rc = GGD_OK;
+        for (int l = L - 1; l >= 1 && rc == GGD_OK; l--) {
+            const LayerInfo &ly = h->lay[l];
+            const bool in_chunk = (l == 1) && !h->dp_fx;       // layer 1 reads the net input from the chunk arrays on one GPU
+            DwwLayer &d = a->layer[a->nlayers++];
+            rc = make_tmap_bf16(&d.a_hi, h->dx_hi[l], h->fx_rows, ly.Np, ly.Np, 32);
+            if (!rc) rc = make_tmap_bf16(&d.a_lo, h->dx_lo[l], h->fx_rows, ly.Np, ly.Np, 32);
+            if (!rc) rc = make_tmap_bf16(&d.b_hi, in_chunk ? h->c_hi : h->act_hi[l - 1], in_chunk ? (long long)h->cap : h->fx_rows, ly.Kp, ly.Kp, 32);
+            if (!rc) rc = make_tmap_bf16(&d.b_lo, in_chunk ? h->c_lo : h->act_lo[l - 1], in_chunk ? (long long)h->cap : h->fx_rows, ly.Kp, ly.Kp, 32);
+            if (!rc) rc = make_tmap_2d(&d.w_map, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 16, 0);
+            if (!rc) rc = make_tmap_2d(&d.d_map, h->Dl + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 16, 0);
+            d.Kp = ly.Kp; d.Np = ly.Np; d.k_slabs = ly.Kp / 64; d.slab_base = base;
+            d.b_rows_from_ctl = in_chunk;
+            d.ev_dx = h->dp_fx ? FX_EV_DX + l : -1; d.ev_y = h->dp_fx ? FX_EV_Y + (l - 1) : -1;
+            d.wc = h->cfg.weightcost;
+            base += ceil_div(ly.Np, 128) * d.k_slabs;
+        }
+        a->total_slabs = base;
+        a->ctl = h->ctl; a->rows_per_bunch = h->M; a->fblocks = h->fx_rows / 32;
+        h->wide_smem = dw_wide_smem(a->fblocks, &a->op_stages, &a->wd_stages);
+        a->mom = h->cfg.momentum; a->lr = h->cfg.lrate; a->Mg = (float)h->Mg;
+        a->advance = 1; a->done_counter = h->dwp_counter; a->hang = h->hang_dev;
+        { const char *ev = getenv("GGD_L2_HINTS"); a->l2_hints = !(ev && atoi(ev) == 0); }
+        a->world = world; a->rank = rank;
+        if (h->dp_fx) {
+            a->flags = h->fx_flags; a->step_counter = h->fx_counters + FXC_STEP; a->error_flag = h->fx_counters + FXC_ERROR;
+            for (int p = 0; p < world; p++) a->peer_flags[p] = (unsigned int *)h->fx_peer[2][p];
+        }
+        cudaError_t e = (rc == GGD_OK) ? cudaMemcpy(h->dww_dev, a, sizeof *a, cudaMemcpyHostToDevice) : cudaSuccess;
+        delete a;
+        GGD_TRY(rc);
+        GGD_CUDA(e);
+        // biases: column sums of dE/dx over the whole minibatch, beside the weight kernel
+        BiasWideArgs &b = h->bias_wide;
+        memset(&b, 0, sizeof b);
+        for (int l = L - 1; l >= 1; l--) {
+            const LayerInfo &ly = h->lay[l];
+            BiasWideLayer &bl = b.layer[b.nlayers++];
+            bl.hi = h->dx_hi[l]; bl.lo = h->dx_lo[l]; bl.ld = ly.Np; bl.N = ly.cur;
+            bl.b = h->P + ly.b_off; bl.db = h->Dl + ly.b_off;
+            bl.ev_dx = h->dp_fx ? FX_EV_DX + l : -1;
+        }
+        b.rows = h->fx_rows; b.mom = h->cfg.momentum; b.lr = h->cfg.lrate; b.Mg = (float)h->Mg;
+        b.world = world; b.rank = rank; b.hang = h->hang_dev;
+        b.flags = h->fx_flags;
+        b.bias_step = h->fx_counters + FXC_BIAS_STEP; b.block_counter = h->fx_counters + FXC_BIAS_BLOCKS; b.error_flag = h->fx_counters + FXC_ERROR;
+    }
+    if (h->dp_fx) {
+        // one push per factor array: my slice -> the same rows of every peer's arena
+        auto make_push = [&](int event, bf16 *hi, bf16 *lo, int l, const bf16 *src_hi, const bf16 *src_lo, long long bunch_stride, int first_of_step) {
+            FxPushArgs &p = h->fx_push[event];
+            memset(&p, 0, sizeof p);
+            const long long bytes = (long long)h->Mp * h->upad[l] * sizeof(bf16);
+            p.seg[0] = {(const uint8_t *)src_hi, bunch_stride, (long long)((uint8_t *)loc(h, hi, l) - h->fx_arena), bytes};
+            p.seg[1] = {(const uint8_t *)src_lo, bunch_stride, (long long)((uint8_t *)loc(h, lo, l) - h->fx_arena), bytes};
+            p.nseg = 2;
+            for (int q = 0; q < world; q++) { p.peer_arena[q] = (uint8_t *)h->fx_peer[0][q]; p.peer_flags[q] = (unsigned int *)h->fx_peer[2][q]; }
+            p.my_flags = h->fx_flags; p.ctl = h->ctl; p.step_counter = h->fx_counters + FXC_STEP;
+            p.block_counter = h->fx_counters + FXC_PUSH_BLOCKS + event; p.error_flag = h->fx_counters + FXC_ERROR; p.hang = h->hang_dev;
+            p.world = world; p.rank = rank; p.event = event; p.wait_done = first_of_step; p.include_self = first_of_step;
+        };
+        // the net-input rows of the current bunch live in the chunk arrays: they are copied into EVERY arena (mine included)
+        make_push(FX_EV_Y + 0, h->act_hi[0], h->act_lo[0], 0, h->c_hi, h->c_lo, (long long)h->M * h->upad[0] * sizeof(bf16), 1);
+        for (int l = 1; l < L - 1; l++) make_push(FX_EV_Y + l, h->act_hi[l], h->act_lo[l], l, loc(h, h->act_hi[l], l), loc(h, h->act_lo[l], l), 0, 0);
+        for (int l = 1; l < L; l++) make_push(FX_EV_DX + l, h->dx_hi[l], h->dx_lo[l], l, loc(h, h->dx_hi[l], l), loc(h, h->dx_lo[l], l), 0, 0);
+    }
     return GGD_OK;
 }
 
@@ -351,90 +416,8 @@ static int ensure_chunk(ggd_handle *h, size_t frames)
     return GGD_OK;
 }
 
-// ---- peer-memory data parallelism: exchange CUDA IPC handles through NCCL, map every peer's arenas -------------
-static int dp_p2p_setup(ggd_handle *h)
-{
-    const int world = h->cfg.world_size, rank = h->cfg.rank;
-    const size_t nflags = (size_t)GGD_MAXLAYER * 2 * DP_MAX_RANKS, ncnt = (size_t)GGD_MAXLAYER * 2 + 2;
-    GGD_CUDA(cudaMalloc(&h->dp_flags, nflags * sizeof(unsigned int)));
-    GGD_CUDA(cudaMemset(h->dp_flags, 0, nflags * sizeof(unsigned int)));
-    GGD_CUDA(cudaMalloc(&h->dp_counters, ncnt * sizeof(unsigned int)));
-    GGD_CUDA(cudaMemset(h->dp_counters, 0, ncnt * sizeof(unsigned int)));
-    void *local[5] = {h->G, h->Phi, h->Plo, h->P, h->dp_flags};
-    cudaIpcMemHandle_t mine[5];
-    for (int k = 0; k < 5; k++) GGD_CUDA(cudaIpcGetMemHandle(&mine[k], local[k]));
-    cudaIpcMemHandle_t *d_all = nullptr, *d_mine = nullptr;
-    GGD_CUDA(cudaMalloc(&d_all, sizeof(mine) * world));
-    GGD_CUDA(cudaMalloc(&d_mine, sizeof(mine)));
-    GGD_CUDA(cudaMemcpy(d_mine, mine, sizeof(mine), cudaMemcpyHostToDevice));
-    GGD_NCCL(ncclAllGather(d_mine, d_all, sizeof(mine), ncclChar, h->comm, h->s_main));
-    GGD_CUDA(cudaStreamSynchronize(h->s_main));
-    std::vector<cudaIpcMemHandle_t> all((size_t)5 * world);
-    GGD_CUDA(cudaMemcpy(all.data(), d_all, sizeof(mine) * world, cudaMemcpyDeviceToHost));
-    cudaFree(d_all); cudaFree(d_mine);
-    for (int p = 0; p < world; p++)
-        for (int k = 0; k < 5; k++) {
-            if (p == rank) { h->peer_base[k][p] = local[k]; continue; }
-            cudaError_t e = cudaIpcOpenMemHandle(&h->peer_base[k][p], all[(size_t)p * 5 + k], cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d, buffer %d): %s", p, k, cudaGetErrorString(e)); return GGD_ECUDA; }
-        }
-    // Ownership: rank r owns the r-th 1/world of EVERY weight matrix and of every bias vector (float4 granularity), so
-    // that each per-layer launch is balanced.  Layer l's launch handles W_l; layer 1's launch (the last of a step) also
-    // handles all biases, whose gradients only exist after the bias-gradient kernel.
-    auto add_piece = [&](DpArgs &a, long long off, long long goff, long long n, float wc, int shadow) {
-        const long long n4 = n / 4, lo = (n4 * rank / world) * 4, hi = (n4 * (rank + 1) / world) * 4;
-        if (hi > lo && a.npieces < 24) a.piece[a.npieces++] = {off + lo, goff + lo, hi - lo, wc, shadow};
-    };
-    for (int l = 1; l < h->L; l++) {
-        DpArgs &a = h->dpa[l];
-        memset(&a, 0, sizeof a);
-        for (int p = 0; p < world; p++) {
-            a.G[p] = (float *)h->peer_base[0][p]; a.hi[p] = (bf16 *)h->peer_base[1][p]; a.lo[p] = (bf16 *)h->peer_base[2][p];
-            a.P[p] = (float *)h->peer_base[3][p];
-            a.flags[p] = (unsigned int *)h->peer_base[4][p] + (size_t)l * 2 * DP_MAX_RANKS;
-        }
-        a.Dl = h->Dl; a.world = world; a.rank = rank;
-        a.mom = h->cfg.momentum; a.lr = h->cfg.lrate; a.Mg = (float)h->Mg;
-        a.step_counter = h->dp_counters + 2 * l; a.block_counter = h->dp_counters + 2 * l + 1;
-        a.error_flag = h->dp_counters + 2 * GGD_MAXLAYER;
-        const LayerInfo &ly = h->lay[l];
-        add_piece(a, (long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1);
-        if (l == 1) {
-            for (int k = 1; k < h->L; k++) add_piece(a, (long long)h->lay[k].b_off, (long long)h->lay[k].gb_off, (long long)h->lay[k].Np, 0.0f, 0);
-            a.ctl = h->ctl;    // last launch of a step: advances the bunch counter
-        }
-    }
-    h->dp_p2p = true;
-    // nobody may enter the first step before every rank has mapped everyone
-    GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
-    GGD_CUDA(cudaStreamSynchronize(h->s_main));
-    return GGD_OK;
-}
-
-// after training, the fp32 master of slice p lives on rank p: pull the other slices before exporting weights
-static int dp_p2p_gather_master(ggd_handle *h)
-{
-    const int world = h->cfg.world_size, rank = h->cfg.rank;
-    // every rank must have finished its last step before its slice is read
-    GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
-    GGD_CUDA(cudaStreamSynchronize(h->s_main));
-    for (int p = 0; p < world; p++) {
-        if (p == rank) continue;
-        for (int l = 1; l < h->L; l++) {
-            const LayerInfo &ly = h->lay[l];
-            const long long n4 = (long long)ly.Kp * ly.Np / 4, lo = (n4 * p / world) * 4, hi = (n4 * (p + 1) / world) * 4;
-            if (hi > lo)
-                GGD_CUDA(cudaMemcpy(h->P + ly.w_off + lo, (const float *)h->peer_base[3][p] + ly.w_off + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault));
-        }
-    }
-    // and nobody may resume training (and overwrite its slice) before everyone has copied
-    GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
-    GGD_CUDA(cudaStreamSynchronize(h->s_main));
-    return GGD_OK;
-}
-
-// ---- push-model data parallelism: buffers, IPC exchange, tile ownership ---------------------------------------------
-static int ipc_exchange(ggd_handle *h, void *const *local, int nbuf, void *(*peer)[DPX_MAX])
+// ---- peer memory: exchange CUDA IPC handles through NCCL, map every peer's buffers ---------------------------------
+static int ipc_exchange(ggd_handle *h, void *const *local, int nbuf, void *(*peer)[FX_MAX])
 {
     const int world = h->cfg.world_size, rank = h->cfg.rank;
     std::vector<cudaIpcMemHandle_t> mine(nbuf), all((size_t)nbuf * world);
@@ -457,6 +440,7 @@ static int ipc_exchange(ggd_handle *h, void *const *local, int nbuf, void *(*pee
     return GGD_OK;
 }
 
+// host-side cross-rank barrier (NCCL allreduce of one float + stream sync)
 static int dp_barrier(ggd_handle *h)
 {
     GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, 1, ncclFloat, ncclSum, h->comm, h->s_main));
@@ -464,100 +448,47 @@ static int dp_barrier(ggd_handle *h)
     return GGD_OK;
 }
 
-static int dp_push_setup(ggd_handle *h)
+// factor-exchange data parallelism: receive slots + flags, IPC exchange of the arenas
+static int dp_fx_setup(ggd_handle *h)
 {
-    const int world = h->cfg.world_size, L = h->L, D = h->units[L - 1];
-    int total = 0;
-    for (int l = 1; l < L; l++) total += ceil_div(h->lay[l].Np, 128) * (h->lay[l].Kp / 64);
-    h->px_total_tiles = total;
-    h->px_slot_tiles = 1;
-    for (int o = 0; o <= world; o++) h->px_own_begin[o] = (int)((long long)total * o / world);
-    for (int o = 0; o < world; o++) h->px_slot_tiles = std::max(h->px_slot_tiles, h->px_own_begin[o + 1] - h->px_own_begin[o]);
-    const size_t rb = (size_t)world * h->px_slot_tiles * 8192, bb = (size_t)world * h->nbias, ab = (size_t)world * D;
-    GGD_CUDA(cudaMalloc(&h->px_rbuf, rb * sizeof(float)));   GGD_CUDA(cudaMemset(h->px_rbuf, 0, rb * sizeof(float)));
-    GGD_CUDA(cudaMalloc(&h->px_bias, bb * sizeof(float)));   GGD_CUDA(cudaMemset(h->px_bias, 0, bb * sizeof(float)));
-    GGD_CUDA(cudaMalloc(&h->px_asum, ab * sizeof(float)));   GGD_CUDA(cudaMemset(h->px_asum, 0, ab * sizeof(float)));
-    GGD_CUDA(cudaMalloc(&h->px_flags, DPX_FLAG_WORDS * sizeof(unsigned int)));
-    GGD_CUDA(cudaMemset(h->px_flags, 0, DPX_FLAG_WORDS * sizeof(unsigned int)));
-    GGD_CUDA(cudaMalloc(&h->px_counters, 8 * sizeof(unsigned int)));
-    GGD_CUDA(cudaMemset(h->px_counters, 0, 8 * sizeof(unsigned int)));
-    GGD_CUDA(cudaMalloc(&h->dpx_dev, sizeof(DpxArgs)));
-    { const char *ev = getenv("GGD_DPX_TRACE"); if (ev && atoi(ev) == 1) { GGD_CUDA(cudaMalloc(&h->px_trace, 2 * 160 * 8 * sizeof(unsigned long long))); GGD_CUDA(cudaMemset(h->px_trace, 0, 2 * 160 * 8 * sizeof(unsigned long long))); } }
-    void *local[7] = {h->px_rbuf, h->px_bias, h->px_asum, h->px_flags, h->Phi, h->Plo, h->P};
-    GGD_TRY(ipc_exchange(h, local, 7, h->px_peer));
-    h->px_k2_smem = dp_push_k2_smem(world, &h->px_k2_stages, &h->px_k2_stage_bytes);
-    GGD_TRY(dp_push_init());
-    std::vector<float *> pp(DPX_MAX, nullptr);
-    std::vector<long long> wo(GGD_MAXLAYER, 0);
-    for (int p = 0; p < world; p++) pp[p] = (float *)h->px_peer[6][p];
-    for (int l = 1; l < L; l++) wo[l - 1] = (long long)h->lay[l].w_off;
-    GGD_CUDA(cudaMalloc(&h->px_peerP_dev, DPX_MAX * sizeof(float *)));
-    GGD_CUDA(cudaMalloc(&h->px_woff_dev, GGD_MAXLAYER * sizeof(long long)));
-    GGD_CUDA(cudaMemcpy(h->px_peerP_dev, pp.data(), DPX_MAX * sizeof(float *), cudaMemcpyHostToDevice));
-    GGD_CUDA(cudaMemcpy(h->px_woff_dev, wo.data(), GGD_MAXLAYER * sizeof(long long), cudaMemcpyHostToDevice));
-    h->dp_push = true;
+    const int world = h->cfg.world_size, D = h->units[h->L - 1];
+    const size_t ab = (size_t)world * D;
+    GGD_CUDA(cudaMalloc(&h->fx_asum, ab * sizeof(float)));   GGD_CUDA(cudaMemset(h->fx_asum, 0, ab * sizeof(float)));
+    GGD_CUDA(cudaMalloc(&h->fx_flags, (size_t)FX_MAX * FX_STRIDE * sizeof(unsigned int)));
+    GGD_CUDA(cudaMemset(h->fx_flags, 0, (size_t)FX_MAX * FX_STRIDE * sizeof(unsigned int)));
+    void *local[3] = {h->fx_arena, h->fx_asum, h->fx_flags};
+    GGD_TRY(ipc_exchange(h, local, 3, h->fx_peer));
+    { const char *ev = getenv("GGD_FX_PUSH_CTAS"); h->fx_push_ctas = (ev && atoi(ev) > 0) ? atoi(ev) : 96; }
     GGD_TRY(dp_barrier(h));    // nobody may enter the first step before every rank has mapped everyone
     return GGD_OK;
 }
 
-// argument block of the push kernels (needs the chunk buffers: rebuilt with the plans)
-static int build_dpx(ggd_handle *h)
+// ---- one training step (forward, loss gradient, backward, update); stream-ordered, no host sync ----
+// side stream: waits for everything queued on `s` so far
+static int fx_fork(ggd_handle *h, cudaStream_t s, int *nfork)
 {
-    const int world = h->cfg.world_size, rank = h->cfg.rank, L = h->L;
-    DpxArgs *a = new DpxArgs();
-    memset(a, 0, sizeof *a);
-    int base = 0, boff = 0;
-    for (int l = 1; l < L; l++) {
-        const LayerInfo &ly = h->lay[l];
-        DpxLayer &d = a->layer[a->nlayers++];
-        d.a_hi = h->dwu[l].b_hi; d.a_lo = h->dwu[l].b_lo;
-        d.b_hi = h->dwu[l].a_hi; d.b_lo = h->dwu[l].a_lo;
-        int rc;
-        if ((rc = make_tmap_2d(&d.w_map, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
-        if ((rc = make_tmap_2d(&d.d_map, h->Dl + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
-        for (int p = 0; p < world; p++) {
-            if ((rc = make_tmap_2d(&d.hi_map[p], (bf16 *)h->px_peer[4][p] + ly.w_off, 0, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
-            if ((rc = make_tmap_2d(&d.lo_map[p], (bf16 *)h->px_peer[5][p] + ly.w_off, 0, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
-            if ((rc = make_tmap_2d(&d.wp_map[p], (float *)h->px_peer[6][p] + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 8, 0))) { delete a; return rc; }
-        }
-        d.dx_hi = h->dx_hi[l]; d.dx_lo = h->dx_lo[l];
-        d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off;
-        d.Kp = ly.Kp; d.Np = ly.Np; d.N = ly.cur; d.k_tiles = ly.Kp / 64; d.tile_base = base;
-        d.b_rows_from_ctl = (l == 1); d.bias_off = boff; d.wc = h->cfg.weightcost;
-        base += ceil_div(ly.Np, 128) * d.k_tiles;
-        boff += ly.Np;
-    }
-    const long long slot_rows = (long long)h->px_slot_tiles * 64;
-    for (int p = 0; p < world; p++) {
-        int rc;
-        // rank p's receive slot for MY tiles (source index = my rank), and my own slot holding source p's tiles
-        if ((rc = make_tmap_2d(&a->push_map[p], (float *)h->px_peer[0][p] + (size_t)rank * slot_rows * 128, 1, slot_rows, 128, 128, 128, 16, 0))) { delete a; return rc; }
-        if ((rc = make_tmap_2d(&a->part_map[p], h->px_rbuf + (size_t)p * slot_rows * 128, 1, slot_rows, 128, 128, 128, 8, 0))) { delete a; return rc; }
-        a->bias_slot[p] = (float *)h->px_peer[1][p];
-        a->asum_slot[p] = (float *)h->px_peer[2][p];
-        a->flags[p] = (unsigned int *)h->px_peer[3][p];
-    }
-    a->counters = h->px_counters; a->error_flag = h->px_counters + 4; a->hang = h->hang_dev; a->ctl = h->ctl;
-    a->trace = h->px_trace;
-    for (int o = 0; o <= world; o++) a->own_begin[o] = h->px_own_begin[o];
-    a->total_tiles = h->px_total_tiles; a->world = world; a->rank = rank; a->nbias = (int)h->nbias;
-    a->rows_per_bunch = h->M; a->M = h->M;
-    a->k2_stages = h->px_k2_stages; a->k2_stage_bytes = h->px_k2_stage_bytes; a->w_f32 = h->w_f32 ? 1 : 0;
-    a->mom = h->cfg.momentum; a->lr = h->cfg.lrate; a->Mg = (float)h->Mg;
-    cudaError_t e = cudaMemcpy(h->dpx_dev, a, sizeof *a, cudaMemcpyHostToDevice);
-    delete a;
-    GGD_CUDA(e);
+    cudaEvent_t e = h->ev_fx[(*nfork)++ % FX_NEVENTS];
+    GGD_CUDA(cudaEventRecord(e, s));
+    GGD_CUDA(cudaStreamWaitEvent(h->s_comm, e, 0));
+    return GGD_OK;
+}
+// factor push of one array on the side stream, after everything queued on `s` so far
+static int fx_push(ggd_handle *h, cudaStream_t s, int event, int *nfork, int *launches)
+{
+    GGD_TRY(fx_fork(h, s, nfork));
+    ProfScope ps(h, KC_PUSH, h->s_comm);
+    launch_factor_push(h->fx_push[event], h->fx_push_ctas, h->s_comm); (*launches)++;
     return GGD_OK;
 }
 
-// ---- one training step (forward, loss gradient, backward, update); stream-ordered, no host sync ----
-static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches, bool train = false)
+static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches, bool train = false, bool fx = false, int *nfork = nullptr)
 {
     const int L = h->L;
     if (h->tensor) {
         for (int l = 1; l < L; l++) {
-            ProfScope ps(h, KC_FWD, s);
-            GGD_TRY(launch_gemm_tc((train && h->fuse_loss && l == L - 1) ? h->fwd_loss : h->fwd[l], s)); (*launches)++;
+            { ProfScope ps(h, KC_FWD, s);
+              GGD_TRY(launch_gemm_tc((train && h->fuse_loss && l == L - 1) ? h->fwd_loss : h->fwd[l], s)); (*launches)++; }
+            if (fx && l < L - 1) GGD_TRY(fx_push(h, s, FX_EV_Y + l, nfork, launches));
         }
     } else {
         launch_simt_gather_in(h->ctl, h->M, h->units[0], h->y32[0], h->upad[0], s); (*launches)++;
@@ -574,24 +505,28 @@ static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches, bool tr
 static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *launches, bool allow_fused = true)
 {
     const bool fused = h->fused && allow_fused && apply_update;
+    const bool fx = h->dp_fx && fused;      // factor exchange: pushes on the side stream, replicated update
     const int L = h->L;
     const LayerInfo &top = h->lay[L - 1];
-    GGD_TRY(enqueue_forward(h, s, launches, true));
+    int nfork = 0;
+    if (h->dp_fx && !fused) { set_error("data-parallel steps need the fused update path"); return GGD_EUNSUPPORTED; }
+    if (fx) GGD_TRY(fx_push(h, s, FX_EV_Y + 0, &nfork, launches));    // net-input rows of this bunch -> every arena
+    GGD_TRY(enqueue_forward(h, s, launches, true, fx, &nfork));
     // ---- fused loss gradient (BP_GPU.cu:408-424); with fuse_loss it already ran in the output layer's epilogue
     LossArgs la;
     memset(&la, 0, sizeof la);
     la.ctl = h->ctl; la.out = h->out32; la.ldo = top.Np; la.M = h->M; la.Mg = h->Mg; la.D = top.cur;
     la.beta = h->cfg.shapefactor; la.ml = (h->cfg.MLflag == 1);
     la.dx32 = h->tensor ? nullptr : h->dx32[L - 1];
-    la.dx_hi = h->tensor ? h->dx_hi[L - 1] : nullptr; la.dx_lo = h->tensor ? h->dx_lo[L - 1] : nullptr;
+    la.dx_hi = h->tensor ? loc(h, h->dx_hi[L - 1], L - 1) : nullptr; la.dx_lo = h->tensor ? loc(h, h->dx_lo[L - 1], L - 1) : nullptr;
     la.ldx = top.Np; la.alpha = h->alpha; la.colsum = h->colsum; la.trace = h->trace;
     if (h->fuse_loss) {
-    } else if (h->dp_push && la.ml) {
+    } else if (h->fx_loss && la.ml) {
         // partial sum|e|^beta exchanged over peer memory inside the loss kernel (no NCCL on the step)
         ProfScope ps(h, KC_LOSS, s);
         la.mode = 3; la.world = h->cfg.world_size; la.rank = h->cfg.rank;
-        la.step_counter = h->px_counters; la.error_flag = h->px_counters + 4;
-        for (int p = 0; p < la.world; p++) { la.asum_slot[p] = (float *)h->px_peer[2][p]; la.lflags[p] = (unsigned int *)h->px_peer[3][p] + DPX_FLAG_LOSS; }
+        la.step_counter = h->fx_counters + FXC_STEP; la.error_flag = h->fx_counters + FXC_ERROR;
+        for (int p = 0; p < la.world; p++) { la.asum_slot[p] = (float *)h->fx_peer[1][p]; la.lflags[p] = (unsigned int *)h->fx_peer[2][p]; }
         launch_loss(la, s); (*launches)++;
     } else if (h->has_comm && la.ml) {
         { ProfScope ps(h, KC_LOSS, s); la.mode = 1; launch_loss(la, s); }
@@ -602,15 +537,17 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         ProfScope ps(h, KC_LOSS, s);
         la.mode = 0; launch_loss(la, s); (*launches)++;
     }
+    if (fx) GGD_TRY(fx_push(h, s, FX_EV_DX + (L - 1), &nfork, launches));
     // ---- backward (BP_GPU.cu:371-438); every GEMM of the step sees the pre-update weights
     for (int l = L - 1; l > 0; l--) {
         const LayerInfo &ly = h->lay[l];
         if (h->tensor) {
-            if (l != 1) { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
-            if (h->dp_push && apply_update) { /* gradient tiles are pushed to their owners after the backward chain */ }
-            else if (fused && h->persist) { /* all layers in one persistent launch after the backward chain */ }
-            else if (fused) { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_update(h->dwu[l], s)); (*launches)++; }
-            else { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
+            if (l != 1) {
+                { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
+                if (fx) GGD_TRY(fx_push(h, s, FX_EV_DX + (l - 1), &nfork, launches));
+            }
+            if (!fused) { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
+            // fused: all layers in one persistent launch after the backward chain
         } else {
             if (l != L - 1) { launch_simt_dsigmoid(h->y32[l], h->dy32[l], h->dx32[l], ly.Np, h->M, ly.cur, s); (*launches)++; }
             if (l != 1) {
@@ -620,40 +557,22 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             launch_simt_gemm(h->y32[l - 1], 1, ly.Kp, h->dx32[l], 1, ly.Np, h->G + ly.w_off, ly.Np, ly.prev, ly.cur, h->M, s);
             (*launches)++;
         }
-        if (h->has_comm && apply_update && h->dp_p2p && l != 1) {
-            // fused NVLink exchange + sharded update of this layer on the communication stream (its blocks use no shared
-            // memory, so they co-reside with the GEMM CTAs of the layers below)
-            GGD_CUDA(cudaEventRecord(h->ev_dw[l], s));
-            GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_dw[l], 0));
-            ProfScope ps(h, KC_UPDATE, h->s_comm);
-            launch_dp_update(h->dpa[l], h->sm_count * 2, h->s_comm); (*launches)++;
-        }
-        if (h->has_comm && apply_update && h->dp_overlap && !h->dp_p2p) {
-            // this layer's weight gradient is complete: allreduce it and apply the update on the communication stream
-            // while the compute stream continues with the layers below
-            GGD_CUDA(cudaEventRecord(h->ev_dw[l], s));
-            GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_dw[l], 0));
-            { ProfScope ps(h, KC_ALLREDUCE, h->s_comm);
-              GGD_NCCL(ncclAllReduce(h->G + ly.w_off, h->G + ly.w_off, (size_t)ly.Kp * ly.Np, ncclFloat, ncclSum, h->comm, h->s_comm)); (*launches)++; }
-            UpdArgs ua;
-            memset(&ua, 0, sizeof ua);
-            ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
-            ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
-            ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
-            { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_update(ua, h->sm_count / 2, h->s_comm); (*launches)++; }
-        }
-    }
-    if (h->dp_push && apply_update) {
-        // K1: every gradient tile -> its owner's receive slot; K2: owners reduce, update, broadcast the bf16 shadows
-        { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_dw_push(h->dpx_dev, h->sm_count, s)); (*launches)++; }
-        { ProfScope ps(h, KC_UPDATE, s); GGD_TRY(launch_reduce_update(h->dpx_dev, h->sm_count, h->px_k2_smem, s)); (*launches)++; }
-        GGD_CUDA(cudaGetLastError());
-        return GGD_OK;
     }
     if (fused && h->persist) {
         // weight gradients + updates of all layers, bias gradients + updates and the bunch counter: one launch
         ProfScope ps(h, KC_DWUPD, s);
         GGD_TRY(launch_dw_persist(h->dwp_dev, h->sm_count, h->w_f32 ? 0 : 1, s)); (*launches)++;
+        GGD_CUDA(cudaGetLastError());
+        return GGD_OK;
+    }
+    if (fused && h->wide) {
+        // biases on the side stream (small, latency-bound) beside the persistent weight kernel; both close the step
+        GGD_TRY(fx_fork(h, s, &nfork));
+        { ProfScope ps(h, KC_BIAS, h->s_comm); launch_bias_wide(h->bias_wide, h->s_comm); (*launches)++; }
+        { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_wide(h->dww_dev, h->sm_count, h->wide_smem, s)); (*launches)++; }
+        cudaEvent_t e = h->ev_fx[nfork++ % FX_NEVENTS];
+        GGD_CUDA(cudaEventRecord(e, h->s_comm));
+        GGD_CUDA(cudaStreamWaitEvent(s, e, 0));
         GGD_CUDA(cudaGetLastError());
         return GGD_OK;
     }
@@ -666,66 +585,22 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
             const LayerInfo &ly = h->lay[l];
             BiasGradLayer &b = ba.layer[ba.nlayers++];
             b.dx32 = h->tensor ? nullptr : h->dx32[l];
-            b.hi = h->tensor ? h->dx_hi[l] : nullptr; b.lo = h->tensor ? h->dx_lo[l] : nullptr;
+            b.hi = h->tensor ? loc(h, h->dx_hi[l], l) : nullptr; b.lo = h->tensor ? loc(h, h->dx_lo[l], l) : nullptr;
             b.ld = ly.Np; b.N = ly.cur; b.dst = h->G + ly.gb_off;
             b.b = h->P + ly.b_off; b.db = h->Dl + ly.b_off;
         }
-        if (fused) {   // biases are updated right here and this is the last kernel of the step
-            ba.apply = 1; ba.mom = h->cfg.momentum; ba.lr = h->cfg.lrate; ba.Mg = (float)h->Mg; ba.ctl = h->ctl;
-        }
         launch_bias_grad(ba, s); (*launches)++;
     }
-    if (fused) { GGD_CUDA(cudaGetLastError()); return GGD_OK; }
-    auto make_upd = [&](UpdArgs &ua) {
+    if (h->has_comm) {
+        // NCCL mode (fp32 validation path, GGD_DP_MODE=nccl): one allreduce of the whole gradient arena
+        ProfScope ps(h, KC_ALLREDUCE, s);
+        GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena + h->nbias, ncclFloat, ncclSum, h->comm, s)); (*launches)++;
+    }
+    if (apply_update) {
+        UpdArgs ua;
         memset(&ua, 0, sizeof ua);
         ua.P = h->P; ua.Dl = h->Dl; ua.G = h->G; ua.Phi = h->Phi; ua.Plo = h->Plo;
         ua.mom = h->cfg.momentum; ua.lr = h->cfg.lrate; ua.Mg = (float)h->Mg;
-    };
-    if (h->has_comm && apply_update && h->dp_p2p) {
-        // layers L-1..2 were exchanged and updated on the communication stream while the backward pass went on (see the
-        // loop above); layer 1 and the biases follow now, then the streams join
-        GGD_CUDA(cudaEventRecord(h->ev_bias, s));
-        GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_bias, 0));
-        { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_dp_update(h->dpa[1], h->sm_count * 2, h->s_comm); (*launches)++; }
-        GGD_CUDA(cudaEventRecord(h->ev_done, h->s_comm));
-        GGD_CUDA(cudaStreamWaitEvent(s, h->ev_done, 0));
-    } else if (h->has_comm && apply_update && !h->dp_overlap) {
-        // one allreduce of the whole gradient arena, then the flat update (no overlap; GGD_DP_OVERLAP=0)
-        { ProfScope ps(h, KC_ALLREDUCE, s);
-          GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena + h->nbias, ncclFloat, ncclSum, h->comm, s)); (*launches)++; }
-        UpdArgs ua;
-        make_upd(ua);
-        for (int l = 1; l < L; l++) {
-            const LayerInfo &ly = h->lay[l];
-            ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
-            ua.seg[ua.nseg++] = {(long long)ly.b_off, (long long)ly.gb_off, (long long)ly.Np, 0.0f, 0};
-        }
-        ua.ctl = h->ctl;
-        ProfScope ps(h, KC_UPDATE, s);
-        launch_update(ua, h->sm_count, s); (*launches)++;
-    } else if (h->has_comm && apply_update) {
-        // Frame-sharded data parallelism: the weight gradients were allreduced and applied layer by
-        // layer on the communication stream while the backward pass went on (see the loop above); what is left is
-        // the packed bias gradients, the bias update, the bunch counter, and the join.
-        GGD_CUDA(cudaEventRecord(h->ev_bias, s));
-        GGD_CUDA(cudaStreamWaitEvent(h->s_comm, h->ev_bias, 0));
-        { ProfScope ps(h, KC_ALLREDUCE, h->s_comm);
-          GGD_NCCL(ncclAllReduce(h->G + h->arena, h->G + h->arena, h->nbias, ncclFloat, ncclSum, h->comm, h->s_comm)); (*launches)++; }
-        UpdArgs ua;
-        make_upd(ua);
-        for (int l = 1; l < L; l++) ua.seg[ua.nseg++] = {(long long)h->lay[l].b_off, (long long)h->lay[l].gb_off, (long long)h->lay[l].Np, 0.0f, 0};
-        ua.ctl = h->ctl;
-        { ProfScope ps(h, KC_UPDATE, h->s_comm); launch_update(ua, 8, h->s_comm); (*launches)++; }
-        GGD_CUDA(cudaEventRecord(h->ev_done, h->s_comm));
-        GGD_CUDA(cudaStreamWaitEvent(s, h->ev_done, 0));
-    } else if (h->has_comm) {
-        ProfScope ps(h, KC_ALLREDUCE, s);
-        GGD_NCCL(ncclAllReduce(h->G, h->G, h->arena + h->nbias, ncclFloat, ncclSum, h->comm, s));
-        (*launches)++;
-        { ProfScope ps2(h, KC_ADVANCE, s); launch_advance(h->ctl, s); (*launches)++; }
-    } else if (apply_update) {
-        UpdArgs ua;
-        make_upd(ua);
         for (int l = 1; l < L; l++) {
             const LayerInfo &ly = h->lay[l];
             ua.seg[ua.nseg++] = {(long long)ly.w_off, (long long)ly.w_off, (long long)ly.Kp * ly.Np, h->cfg.weightcost, 1};
@@ -824,6 +699,9 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     h->stats.steps = nb; h->stats.launches = 0;
     h->losses.assign(nb, 0.0f);
     if (nb == 0) { h->stats.device_ms = 0; return GGD_OK; }
+    // data parallel: every rank enters the chunk together (each rank feeds its own loader / disk; the in-kernel peer waits
+    // are bounded, so skew between ranks must be absorbed HERE, on the host, where waiting is free)
+    if (h->has_comm) GGD_TRY(dp_barrier(h));
     GGD_TRY(set_ctl(h, d_in, d_targ));
     GGD_CUDA(cudaMemsetAsync(h->trace, 0, h->trace_cap * sizeof(double), h->s_main));
     GGD_CUDA(cudaEventRecord(h->ev1, h->s_main));
@@ -873,33 +751,9 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     h->stats.device_ms = ms;
     for (int b = 0; b < nb; b++) h->losses[b] = (float)tr[b];
     h->stats.d2h_bytes = nb * sizeof(double);
-    if (h->dp_push && h->px_trace) {
-        // per-CTA phase stamps of the LAST step's two exchange kernels (tuning aid, GGD_DPX_TRACE=1)
-        const int G = h->sm_count;
-        std::vector<unsigned long long> tr2((size_t)2 * G * 8);
-        GGD_CUDA(cudaMemcpy(tr2.data(), h->px_trace, tr2.size() * 8, cudaMemcpyDeviceToHost));
-        unsigned long long t0 = ~0ull;
-        for (int c = 0; c < G; c++) if (tr2[(size_t)c * 8]) t0 = std::min(t0, tr2[(size_t)c * 8]);
-        for (int k = 0; k < 2; k++) {
-            fprintf(stderr, "[rank %d] %s:", h->cfg.rank, k ? "K2 reduce_update" : "K1 dw_push");
-            for (int sl = 0; sl < 7; sl++) {
-                std::vector<double> v;
-                for (int c = 0; c < G; c++) { const unsigned long long x = tr2[((size_t)k * G + c) * 8 + sl]; if (x) v.push_back((double)(x - t0) * 1e-3); }
-                if (v.empty()) continue;
-                std::sort(v.begin(), v.end());
-                fprintf(stderr, " s%d[min %.1f med %.1f max %.1f]", sl, v.front(), v[v.size() / 2], v.back());
-            }
-            fprintf(stderr, " us\n");
-        }
-    }
-    if (h->dp_push) {
+    if (h->dp_fx) {
         unsigned int err = 0;
-        GGD_CUDA(cudaMemcpy(&err, h->px_counters + 4, sizeof err, cudaMemcpyDeviceToHost));
-        if (err) { set_error("data-parallel step: rank %u did not arrive within the timeout (ranks must train the same number of bunches)", err - 1); return GGD_ENCCL; }
-    }
-    if (h->dp_p2p) {
-        unsigned int err = 0;
-        GGD_CUDA(cudaMemcpy(&err, h->dp_counters + 2 * GGD_MAXLAYER, sizeof err, cudaMemcpyDeviceToHost));
+        GGD_CUDA(cudaMemcpy(&err, h->fx_counters + FXC_ERROR, sizeof err, cudaMemcpyDeviceToHost));
         if (err) { set_error("data-parallel step: rank %u did not arrive within the timeout (ranks must train the same number of bunches)", err - 1); return GGD_ENCCL; }
     }
     return GGD_OK;
@@ -943,21 +797,31 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     h->L = cfg->numlayers; h->M = cfg->bunchsize; h->Mp = round_up(h->M, 128);
     h->sm_count = prop.multiProcessorCount;
     h->tensor = (cfg->precision == GGD_PREC_BF16X3);
-    h->fused = h->tensor && !(cfg->world_size > 1) && !(cfg->flags & GGD_FLAG_UNFUSED_UPDATE);
-    {
-        const char *ev = getenv("GGD_DW_PERSIST");   // 0: per-layer dw_update launches (tuning / A-B only)
-        h->persist = h->fused && h->Mp == 128 && !(ev && atoi(ev) == 0);
-    }
-    {
-        // GGD_W_F32: 1 = GEMMs split the fp32 master weights in-kernel (no shadows; update kernel 57 -> 44 us, GEMMs +1.3 us
-        // each: 124.7 -> 121.9 us per step on one GPU), 0 = bf16 hi/lo shadows maintained by the update kernels.  Default:
-        // on for one GPU; off for data parallelism, where the exchange kernels are NVLink-bound and only the GEMM cost shows
-        // (195 vs 184 us per step at N = 2).
-        const char *ev = getenv("GGD_W_F32");
-        h->w_f32 = h->tensor && (ev ? atoi(ev) != 0 : !(cfg->world_size > 1));
-    }
     const int world = cfg->world_size > 1 ? cfg->world_size : 1;
+    {
+        // data parallelism: factor exchange over NVLink peer memory (default, tensor path) or NCCL allreduce of the gradient
+        // arena (GGD_DP_MODE=nccl, the fp32 validation path, GGD_FLAG_UNFUSED_UPDATE)
+        const char *dm = getenv("GGD_DP_MODE");
+        const bool want_nccl = dm && !strcmp(dm, "nccl");
+        h->dp_fx = world > 1 && world <= FX_MAX && h->tensor && !want_nccl && !(cfg->flags & GGD_FLAG_UNFUSED_UPDATE);
+        h->fx_loss = h->dp_fx && cfg->layersizes[cfg->numlayers - 1] <= 16 * LOSS_FLAGS_PER_RANK;   // one flag per 16-column chunk
+    }
+    h->fused = h->tensor && !(cfg->flags & GGD_FLAG_UNFUSED_UPDATE) && (world == 1 || h->dp_fx);
+    {
+        const char *ev = getenv("GGD_DW_PERSIST");   // 0: the wide kernel also at 128 frames (tuning / A-B only)
+        h->persist = h->fused && world == 1 && h->Mp == 128 && !(ev && atoi(ev) == 0);
+        h->wide = h->fused && !h->persist;
+    }
+    {
+        // GGD_W_F32: 1 (default) = GEMMs split the fp32 master weights in-kernel (no shadows; update kernel 57 -> 44 us, GEMMs
+        // +1.3 us each: 124.7 -> 121.9 us per step on one GPU), 0 = bf16 hi/lo shadows maintained by the update kernels
+        // (dw_persist / update_kernel only: the wide kernel keeps no shadows)
+        const char *ev = getenv("GGD_W_F32");
+        h->w_f32 = h->tensor && ((ev ? atoi(ev) != 0 : true) || h->wide);
+    }
     h->Mg = h->M * world;
+    h->fx_rows = h->dp_fx ? world * h->Mp : h->Mp;
+    h->loc_row = h->dp_fx ? cfg->rank * h->Mp : 0;
     size_t off = 0;
     for (int i = 0; i < h->L; i++) { h->units[i] = cfg->layersizes[i]; h->upad[i] = round_up(h->units[i], 64); }
     for (int l = 1; l < h->L; l++) {
@@ -975,22 +839,30 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev_c0)); CK(cudaEventCreate(&h->ev_c1));
     { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); CK(cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi)); }
-    for (int l = 0; l < GGD_MAXLAYER; l++) CK(cudaEventCreateWithFlags(&h->ev_dw[l], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_bias, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    for (int k = 0; k < FX_NEVENTS; k++) CK(cudaEventCreateWithFlags(&h->ev_fx[k], cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev2));
     CK(cudaMalloc(&h->P, off * sizeof(float))); CK(cudaMalloc(&h->Dl, off * sizeof(float))); CK(cudaMalloc(&h->G, (off + h->nbias) * sizeof(float)));
     CK(cudaMalloc(&h->Phi, off * sizeof(bf16))); CK(cudaMalloc(&h->Plo, off * sizeof(bf16)));
     CK(cudaMemset(h->P, 0, off * sizeof(float))); CK(cudaMemset(h->Dl, 0, off * sizeof(float))); CK(cudaMemset(h->G, 0, (off + h->nbias) * sizeof(float)));
     CK(cudaMemset(h->Phi, 0, off * sizeof(bf16))); CK(cudaMemset(h->Plo, 0, off * sizeof(bf16)));
+    if (h->tensor) {
+        // factor arena: act_hi, act_lo, dx_hi, dx_lo of every layer, [fx_rows][upad] bf16 each (1 KB aligned)
+        size_t o = 0;
+        auto carve = [&](int l) { const size_t at = o; o += (((size_t)h->fx_rows * h->upad[l] * sizeof(bf16)) + 1023) & ~(size_t)1023; return at; };
+        size_t at[GGD_MAXLAYER][4];
+        for (int l = 0; l < h->L; l++) for (int k = 0; k < 4; k++) at[l][k] = carve(l);
+        h->fx_bytes = o;
+        CK(cudaMalloc(&h->fx_arena, o));
+        CK(cudaMemset(h->fx_arena, 0, o));
+        for (int l = 0; l < h->L; l++) {
+            h->act_hi[l] = (bf16 *)(h->fx_arena + at[l][0]); h->act_lo[l] = (bf16 *)(h->fx_arena + at[l][1]);
+            h->dx_hi[l] = (bf16 *)(h->fx_arena + at[l][2]); h->dx_lo[l] = (bf16 *)(h->fx_arena + at[l][3]);
+        }
+    }
+    CK(cudaMalloc(&h->fx_counters, FXC_WORDS * sizeof(unsigned int))); CK(cudaMemset(h->fx_counters, 0, FXC_WORDS * sizeof(unsigned int)));
     for (int l = 0; l < h->L; l++) {
         const size_t n = (size_t)h->Mp * h->upad[l];
         if (h->tensor) {
-            if (l >= 1) {
-                CK(cudaMalloc(&h->act_hi[l], n * sizeof(bf16))); CK(cudaMalloc(&h->act_lo[l], n * sizeof(bf16)));
-                CK(cudaMalloc(&h->dx_hi[l], n * sizeof(bf16))); CK(cudaMalloc(&h->dx_lo[l], n * sizeof(bf16)));
-                CK(cudaMemset(h->act_hi[l], 0, n * sizeof(bf16))); CK(cudaMemset(h->act_lo[l], 0, n * sizeof(bf16)));
-                CK(cudaMemset(h->dx_hi[l], 0, n * sizeof(bf16))); CK(cudaMemset(h->dx_lo[l], 0, n * sizeof(bf16)));
-            }
         } else {
             CK(cudaMalloc(&h->x32[l], n * sizeof(float))); CK(cudaMalloc(&h->y32[l], n * sizeof(float)));
             CK(cudaMalloc(&h->dy32[l], n * sizeof(float))); CK(cudaMalloc(&h->dx32[l], n * sizeof(float)));
@@ -1004,7 +876,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     CK(cudaMalloc(&h->alpha, D * sizeof(float))); CK(cudaMalloc(&h->colsum, D * sizeof(float)));
     CK(cudaMemset(h->alpha, 0, D * sizeof(float))); CK(cudaMemset(h->colsum, 0, D * sizeof(float)));
     CK(cudaMalloc(&h->ctl, sizeof(StepCtl))); CK(cudaMemset(h->ctl, 0, sizeof(StepCtl)));
-    CK(cudaMalloc(&h->dwp_dev, sizeof(DwpArgs))); CK(cudaMalloc(&h->dwp_counter, sizeof(unsigned int)));
+    CK(cudaMalloc(&h->dwp_dev, sizeof(DwpArgs))); CK(cudaMalloc(&h->dww_dev, sizeof(DwwArgs))); CK(cudaMalloc(&h->dwp_counter, sizeof(unsigned int)));
     CK(cudaMemset(h->dwp_counter, 0, sizeof(unsigned int)));
     CK(cudaHostAlloc(&h->hang_host, HANG_WORDS * sizeof(unsigned int), cudaHostAllocMapped)); memset(h->hang_host, 0, HANG_WORDS * sizeof(unsigned int));
     CK(cudaHostGetDevicePointer(&h->hang_dev, h->hang_host, 0));
@@ -1017,36 +889,22 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
         launch_split_rows(h->P + ly.w_off, ly.Kp, ly.Np, h->Phi + ly.w_off, h->Plo + ly.w_off, ly.Np, 0);
     }
     CK(cudaDeviceSynchronize());
-    if (h->tensor) { int rc = gemm_tc_init(); if (rc == GGD_OK) rc = dw_update_init(); if (rc == GGD_OK) rc = dw_persist_init(); if (rc != GGD_OK) return fail(rc); }
+    if (h->tensor) { int rc = gemm_tc_init(); if (rc == GGD_OK) rc = dw_persist_init(); if (rc == GGD_OK) rc = dw_wide_init(); if (rc != GGD_OK) return fail(rc); }
     if (world > 1) {
         if (!cfg->nccl_unique_id) { set_error("world_size > 1 needs nccl_unique_id"); return fail(GGD_EINVAL); }
         ncclUniqueId id;
         memcpy(&id, cfg->nccl_unique_id, sizeof id);
-        // Measured on 2 x B200 (profiles/r01_dp_sweep_n2.log): one allreduce of the whole gradient arena after the
-        // backward pass (310 us/step) beats per-layer allreduces overlapped with the backward GEMMs (385-580 us/step):
-        // the GEMMs hold every SM with ~190 KB of shared memory, so NCCL's CTAs only run in the gaps.  Both schedules
-        // stay selectable (GGD_DP_OVERLAP, GGD_NCCL_MAX_CTAS) for tuning.
         ncclConfig_t ncfg = NCCL_CONFIG_INITIALIZER;
         const char *mc = getenv("GGD_NCCL_MAX_CTAS");
         if (mc) { ncfg.maxCTAs = atoi(mc); ncfg.minCTAs = ncfg.maxCTAs < 4 ? ncfg.maxCTAs : 4; }
         ncclResult_t r = ncclCommInitRankConfig(&h->comm, world, id, cfg->rank, &ncfg);
         if (r != ncclSuccess) { set_error("ncclCommInitRankConfig: %s", ncclGetErrorString(r)); return fail(GGD_ENCCL); }
         h->has_comm = true;
-        const char *ov = getenv("GGD_DP_OVERLAP");
-        h->dp_overlap = ov ? atoi(ov) : 0;
-        // GGD_DP_MODE: push (default when the bunch is one reduction tile) | pull (dp_update.cu) | nccl (allreduce)
-        const char *dm = getenv("GGD_DP_MODE");
-        const char *pm = getenv("GGD_DP_P2P");
-        const bool want_nccl = (dm && !strcmp(dm, "nccl")) || (pm && atoi(pm) == 0);
-        const bool want_pull = dm && !strcmp(dm, "pull");
-        if (!want_nccl && world <= DP_MAX_RANKS && h->tensor) {   // (the fp32 validation path reads the master weights)
-            int rc = (!want_pull && h->Mp == 128) ? dp_push_setup(h) : dp_p2p_setup(h);
-            if (rc != GGD_OK) return fail(rc);
-        }
+        if (h->dp_fx) { int rc = dp_fx_setup(h); if (rc != GGD_OK) return fail(rc); }
     }
     {
         const char *ev = getenv("GGD_FUSE_LOSS");   // 0: separate loss kernel (A-B / tuning)
-        h->fuse_loss = h->tensor && h->Mp == 128 && (world == 1 || h->dp_push) && !(ev && atoi(ev) == 0);
+        h->fuse_loss = h->tensor && h->Mp == 128 && (world == 1 || h->fx_loss) && !(ev && atoi(ev) == 0);
     }
 #undef CK
     *out = h;
@@ -1064,29 +922,19 @@ int ggd_destroy(ggd_handle *h)
     if (h->ev_c1) cudaEventDestroy(h->ev_c1);
     free_chunk(h);
     for (auto &kv : h->pinned) if (kv.second) cudaHostUnregister(const_cast<void *>(kv.first));
-    if (h->dp_p2p)
+    if (h->dp_fx && h->fx_peer[0][h->cfg.rank])
         for (int p = 0; p < h->cfg.world_size; p++)
-            for (int k = 0; k < 5; k++) if (p != h->cfg.rank && h->peer_base[k][p]) cudaIpcCloseMemHandle(h->peer_base[k][p]);
-    if (h->dp_push)
-        for (int p = 0; p < h->cfg.world_size; p++)
-            for (int k = 0; k < 7; k++) if (p != h->cfg.rank && h->px_peer[k][p]) cudaIpcCloseMemHandle(h->px_peer[k][p]);
-    cudaFree(h->px_rbuf); cudaFree(h->px_bias); cudaFree(h->px_asum); cudaFree(h->px_flags); cudaFree(h->px_counters); cudaFree(h->dpx_dev);
-    cudaFree(h->px_peerP_dev); cudaFree(h->px_woff_dev); cudaFree(h->px_trace);
+            for (int k = 0; k < 3; k++) if (p != h->cfg.rank && h->fx_peer[k][p]) cudaIpcCloseMemHandle(h->fx_peer[k][p]);
+    cudaFree(h->fx_asum); cudaFree(h->fx_flags); cudaFree(h->fx_counters); cudaFree(h->fx_arena); cudaFree(h->dww_dev);
     cudaFree(h->r_fea); cudaFree(h->r_targ); cudaFree(h->r_first); cudaFree(h->r_norm);
-    cudaFree(h->dp_flags); cudaFree(h->dp_counters);
     if (h->has_comm) ncclCommDestroy(h->comm);
     cudaFree(h->P); cudaFree(h->Dl); cudaFree(h->G); cudaFree(h->Phi); cudaFree(h->Plo);
-    for (int l = 0; l < GGD_MAXLAYER; l++) {
-        cudaFree(h->act_hi[l]); cudaFree(h->act_lo[l]); cudaFree(h->dx_hi[l]); cudaFree(h->dx_lo[l]);
-        cudaFree(h->x32[l]); cudaFree(h->y32[l]); cudaFree(h->dy32[l]); cudaFree(h->dx32[l]);
-    }
+    for (int l = 0; l < GGD_MAXLAYER; l++) { cudaFree(h->x32[l]); cudaFree(h->y32[l]); cudaFree(h->dy32[l]); cudaFree(h->dx32[l]); }
     cudaFree(h->out32); cudaFree(h->alpha); cudaFree(h->colsum); cudaFree(h->ctl); cudaFree(h->dwp_dev); cudaFree(h->dwp_counter); if (h->hang_host) cudaFreeHost(h->hang_host);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
-    for (int l = 0; l < GGD_MAXLAYER; l++) if (h->ev_dw[l]) cudaEventDestroy(h->ev_dw[l]);
-    if (h->ev_bias) cudaEventDestroy(h->ev_bias);
-    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (int k = 0; k < FX_NEVENTS; k++) if (h->ev_fx[k]) cudaEventDestroy(h->ev_fx[k]);
     if (h->s_comm) cudaStreamDestroy(h->s_comm);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     delete h;
@@ -1122,6 +970,18 @@ int ggd_train(ggd_handle *h, int n_frames, const float *in, const float *targ)
     float ms = 0;
     if (n_frames / h->M > 0) cudaEventElapsedTime(&ms, h->ev_c0, h->ev_c1);
     h->stats.h2d_ms = ms; h->stats.h2d_bytes = bi + bt;   // copy-stream time; it overlaps the steps of the earlier pieces
+    return GGD_OK;
+}
+
+int ggd_release_host(ggd_handle *h, const void *host_ptr)
+{
+    if (!h) { set_error("ggd_release_host: null handle"); return GGD_EINVAL; }
+    auto it = h->pinned.find(host_ptr);
+    if (it == h->pinned.end()) return GGD_OK;
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+    if (it->second) cudaHostUnregister(const_cast<void *>(host_ptr));
+    h->pinned.erase(it);
     return GGD_OK;
 }
 
@@ -1290,14 +1150,7 @@ int ggd_get_weights(ggd_handle *h, float *const *weights, float *const *bias)
     if (!h || !weights || !bias) { set_error("ggd_get_weights: bad argument"); return GGD_EINVAL; }
     GGD_CUDA(cudaSetDevice(h->cfg.gpu));
     GGD_CUDA(cudaStreamSynchronize(h->s_main));
-    if (h->dp_p2p) GGD_TRY(dp_p2p_gather_master(h));
-    if (h->dp_push && !h->w_f32) {
-        // the fp32 master of a tile lives on its owner: pull the foreign tiles (between two cross-rank barriers)
-        GGD_TRY(dp_barrier(h));
-        launch_gather_master(h->dpx_dev, h->px_peerP_dev, h->px_woff_dev, h->sm_count * 2, h->s_main);
-        GGD_CUDA(cudaStreamSynchronize(h->s_main));
-        GGD_TRY(dp_barrier(h));
-    }
+    // (data parallel: every rank holds the full, bit-identical fp32 master weights -- nothing to gather)
     for (int l = 1; l < h->L; l++) {
         const LayerInfo &ly = h->lay[l];
         GGD_CUDA(cudaMemcpy2D(weights[l], ly.cur * sizeof(float), h->P + ly.w_off, ly.Np * sizeof(float), ly.cur * sizeof(float), ly.prev, cudaMemcpyDeviceToHost));
@@ -1381,12 +1234,12 @@ int ggd_debug_read(ggd_handle *h, int what, int layer, float *dst)
     const LayerInfo &ly = h->lay[layer];
     switch (what) {
     case 1:
-        if (h->tensor) return read_pair(h, h->dx_hi[layer], h->dx_lo[layer], ly.Np, h->M, ly.cur, dst);
+        if (h->tensor) return read_pair(h, loc(h, h->dx_hi[layer], layer), loc(h, h->dx_lo[layer], layer), ly.Np, h->M, ly.cur, dst);
         GGD_CUDA(cudaMemcpy2D(dst, ly.cur * sizeof(float), h->dx32[layer], ly.Np * sizeof(float), ly.cur * sizeof(float), h->M, cudaMemcpyDeviceToHost));
         return GGD_OK;
     case 2:
         if (layer == L - 1) { set_error("layer %d is linear: read what=0", layer); return GGD_EINVAL; }
-        if (h->tensor) return read_pair(h, h->act_hi[layer], h->act_lo[layer], ly.Np, h->M, ly.cur, dst);
+        if (h->tensor) return read_pair(h, loc(h, h->act_hi[layer], layer), loc(h, h->act_lo[layer], layer), ly.Np, h->M, ly.cur, dst);
         GGD_CUDA(cudaMemcpy2D(dst, ly.cur * sizeof(float), h->y32[layer], ly.Np * sizeof(float), ly.cur * sizeof(float), h->M, cudaMemcpyDeviceToHost));
         return GGD_OK;
     case 3:
@@ -1446,9 +1299,8 @@ int ggd_debug_trace_step(ggd_handle *h, const float *in, const float *targ, int 
     }
     for (int l = L - 1; l > 0; l--) {
         if (l != 1) items.push_back({2, h->dxp[l].splits * h->dxp[l].tiles_i * h->dxp[l].tiles_j, &h->dxp[l].args.trace});
-        if (fused && h->fused && h->persist) continue;     // the persistent gradient+update kernel carries no stamps
-        if (fused && h->fused) items.push_back({9, h->dwu[l].tiles_i * h->dwu[l].tiles_j, &h->dwu[l].args.trace});
-        else items.push_back({3, h->dwp[l].tiles_i * h->dwp[l].tiles_j, &h->dwp[l].args.trace});
+        if (fused && h->fused) continue;     // the persistent gradient+update kernels carry no stamps
+        items.push_back({3, h->dwp[l].tiles_i * h->dwp[l].tiles_j, &h->dwp[l].args.trace});
     }
     size_t total = 0;
     for (auto &it : items) total += (size_t)it.ctas * 16;

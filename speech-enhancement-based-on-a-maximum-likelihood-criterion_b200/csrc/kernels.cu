@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
                     __syncwarp();
                     if (tx == 0)
                         for (int p = 0; p < a.world; p++)
-                            if (p != a.rank) st_release_sys_u32(a.lflags[p] + a.rank * 16 + blockIdx.x, step);
+                            if (p != a.rank) st_release_sys_u32(a.lflags[p] + a.rank * FX_STRIDE + FX_EV_LOSS + blockIdx.x, step);
                     if (tx < a.world && tx != a.rank) {
-                        const unsigned int *f = a.lflags[a.rank] + tx * 16 + blockIdx.x;
+                        const unsigned int *f = a.lflags[a.rank] + tx * FX_STRIDE + FX_EV_LOSS + blockIdx.x;
                         const long long t0 = clock64();
                         while ((int)(ld_acquire_sys_u32(f) - step) < 0) {
                             if (clock64() - t0 > (1ll << 32)) { *a.error_flag = 1u + tx; break; }

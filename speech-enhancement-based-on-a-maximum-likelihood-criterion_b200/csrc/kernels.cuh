@@ -8,6 +8,17 @@ namespace ggd {
 
 typedef __nv_bfloat16 bf16;
 
+// ---- flag layout of the data-parallel exchanges over NVLink peer memory (dp_factor.cuh) ----------------------------
+constexpr int FX_MAX = 8;                 // ranks
+constexpr int LOSS_FLAGS_PER_RANK = 32;   // alpha exchange: one flag per source rank and 16-column chunk (32-column block in loss_kernel)
+// Flag block of one rank: [source rank][FX_STRIDE] 32-bit words, written by the peers with st.release.sys, values = step.
+//   [FX_EV_Y + l]    source's activations y_l of this step have landed in my factor arena (l = 0: the net-input rows)
+//   [FX_EV_DX + l]   source's dE/dx_l of this step have landed
+//   [FX_EV_DONE]     source has finished step `value`: it no longer reads its factor arena (my next pushes may overwrite it)
+//   [FX_EV_LOSS + c] source's partial sum_m|e|^beta of column chunk c
+constexpr int FX_EV_Y = 0, FX_EV_DX = 10, FX_EV_DONE = 20, FX_EV_LOSS = 32, FX_STRIDE = 64;
+static_assert(FX_EV_LOSS + LOSS_FLAGS_PER_RANK <= FX_STRIDE, "flag block layout");
+
 // Device-side step control block: read by every kernel of a step so that one captured CUDA graph
 // can be replayed for every bunch of a chunk (the bunch index advances on the device).
 struct StepCtl {
@@ -52,9 +63,9 @@ struct LossArgs {
     double *trace;      // per-bunch loss trace, indexed by ctl->bunch_idx (may be NULL)
     int mode;           // 0 = fused single pass-pair, 1 = column sums only, 2 = gradient from `colsum`,
                         // 3 = data-parallel in ONE kernel: partial column sums are stored into every rank's slot over
-                        //     NVLink peer memory, flagged, and summed in rank order (dp_push.cuh)
+                        //     NVLink peer memory, flagged, and summed in rank order (dp_factor.cuh)
     float *asum_slot[8];            // mode 3: every rank's receive area [world][D]
-    unsigned int *lflags[8];        // mode 3: every rank's loss flags [world][16] (one per source rank and block)
+    unsigned int *lflags[8];        // mode 3: every rank's flag block [world][FX_STRIDE]; loss flags at FX_EV_LOSS + block
     const unsigned int *step_counter;   // mode 3: completed data-parallel steps (flag value = *step_counter + 1)
     unsigned int *error_flag;
     int world, rank;

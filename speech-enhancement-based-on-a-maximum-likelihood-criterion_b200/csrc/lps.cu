@@ -1,5 +1,12 @@
-// lps.cu -- B200 LPS front end (include/lps_b200.h).
+// lps.cu -- B200 LPS front end (include/lps_b200.h).  Two kernels:
 //
+// lps_fast_kernel (default): register-resident FFT.  A 512-point real transform is a 256-point complex transform of
+// z[n] = x[2n] + i x[2n+1] plus a split step; one warp = one frame, 8 complex points per lane, radix 8 x 8 x 4:
+// radix-8 butterflies in registers, one shared-memory transpose, radix-8 again, the last radix-4 across lane quads
+// with shuffles, a second transpose for the conjugate-pair split, hardware log2.  fp32 with exactly rounded twiddles;
+// ~450 warp instructions per frame against ~6 000 for the schedule interpreter below.
+//
+// lps_kernel (LPS_FLAG_EXACT): the reference's butterfly network itself, bit-identical spectrum.
 // One warp per frame.  The frame's 512 windowed samples live in shared memory; the warp executes the
 // reference's in-place split-radix real FFT (FEfunc.c:146-293) as a precomputed butterfly SCHEDULE:
 // the host walks the reference's loop nest once and records, stage by stage, every butterfly with its
@@ -206,6 +213,170 @@ __global__ void __launch_bounds__(WARPS * 32) lps_kernel(const LpsArgs a)
         }
         __syncwarp();
     }
+}
+
+
+// =====================================================================================================================
+// Fast path
+// =====================================================================================================================
+constexpr int XSTR = 36;                 // row pitch (float2) of the first transpose: conflict-free per half-warp
+struct FastTab {
+    float win[N];                        // Hamming window (FEfunc.c:80-87), in double then float like the reference
+    float2 tw1[8][32];                   // w256^(b*k1)   [k1][b]
+    float2 tw2[8][4];                    // w32^(d*p)     [p][d]
+    float2 post[LPS_BINS];               // (cos, sin)(2 pi k / 512)
+    float floor_fb;                      // (float)exp(-50.0)
+};
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// a * (c - i s)  with tw = (c, s): forward-transform twiddle e^{-i theta}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 tw)
+{
+    return make_float2(fmaf(a.x, tw.x, a.y * tw.y), fmaf(a.y, tw.x, -a.x * tw.y));
+}
+// 8-point forward DFT in registers, natural order in and out
+__device__ __forceinline__ void fft8(float2 *v)
+{
+    const float R = 0.70710678118654752440f;
+    float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+    float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+    // b_j *= w8^j:  w8 = (1 - i)/sqrt2, w8^2 = -i, w8^3 = (-1 - i)/sqrt2
+    b1 = make_float2((b1.x + b1.y) * R, (b1.y - b1.x) * R);
+    b2 = make_float2(b2.y, -b2.x);
+    b3 = make_float2((b3.y - b3.x) * R, -(b3.x + b3.y) * R);
+    // two 4-point DFTs: even outputs from a, odd outputs from b
+    {
+        const float2 s0 = cadd(a0, a2), s1 = csub(a0, a2), s2 = cadd(a1, a3), t = csub(a1, a3);
+        const float2 s3 = make_float2(t.y, -t.x);
+        v[0] = cadd(s0, s2); v[4] = csub(s0, s2); v[2] = cadd(s1, s3); v[6] = csub(s1, s3);
+    }
+    {
+        const float2 s0 = cadd(b0, b2), s1 = csub(b0, b2), s2 = cadd(b1, b3), t = csub(b1, b3);
+        const float2 s3 = make_float2(t.y, -t.x);
+        v[1] = cadd(s0, s2); v[5] = csub(s0, s2); v[3] = cadd(s1, s3); v[7] = csub(s1, s3);
+    }
+}
+
+struct FastArgs {
+    const int16_t *pcm;
+    const long long *utt_sample_off, *utt_frame_off;
+    int n_utts;
+    long long total_frames;
+    float *out;
+    const float *mean, *dvar;
+    int flags;
+    const FastTab *tab;
+};
+
+constexpr int FWARPS = 8;
+__global__ void __launch_bounds__(FWARPS * 32, 2) lps_fast_kernel(const FastArgs a)
+{
+    __shared__ float2 xch[FWARPS][8 * XSTR];          // transpose 1: [k1][b]; transpose 2: Z[k] at k + 4 (k >> 6)
+    __shared__ float2 s_post[LPS_BINS];
+    __shared__ float2 s_tw2[8][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < LPS_BINS; i += blockDim.x) s_post[i] = a.tab->post[i];
+    if (threadIdx.x < 32) s_tw2[threadIdx.x >> 2][threadIdx.x & 3] = a.tab->tw2[threadIdx.x >> 2][threadIdx.x & 3];
+    // per-lane constants: window at samples 64 a + 2 lane (+1), first-pass twiddles w256^(lane*k1)
+    float2 win[8], tw1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        win[j] = make_float2(a.tab->win[64 * j + 2 * lane], a.tab->win[64 * j + 2 * lane + 1]);
+        tw1[j] = a.tab->tw1[j][lane];
+    }
+    const float floor_fb = a.tab->floor_fb;
+    __syncthreads();
+    float2 *xs = xch[warp];
+    const int k1 = lane >> 2, d = lane & 3;              // second-pass role of this lane
+    const int q = ((d & 1) << 1) | (d >> 1);             // output index of the cross-lane radix-4 (bit-reversed d)
+
+    for (long long f = (long long)blockIdx.x * FWARPS + warp; f < a.total_frames; f += (long long)gridDim.x * FWARPS) {
+        int lo = 0, hi = a.n_utts;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.utt_frame_off[mid] <= f) lo = mid; else hi = mid;
+        }
+        const long long base = a.utt_sample_off[lo] + (f - a.utt_frame_off[lo]) * LPS_FRAME_SHIFT;
+        const int16_t *src = a.pcm + base + 2 * lane;
+        // z[32 j + lane] = x[64 j + 2 lane] + i x[64 j + 2 lane + 1], windowed (ReadWave fileio.c:268-282, Window FEfunc.c:106-118)
+        float2 v[8];
+        if ((base & 1) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const unsigned int w = __ldg(reinterpret_cast<const unsigned int *>(src + 64 * j));
+                v[j] = make_float2((float)(short)(w & 0xFFFFu) * win[j].x, (float)(short)(w >> 16) * win[j].y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = make_float2((float)__ldg(src + 64 * j) * win[j].x, (float)__ldg(src + 64 * j + 1) * win[j].y);
+        }
+        // pass 1: DFT over j (stride-32 points), twiddle w256^(lane*k1), transpose through shared memory
+        fft8(v);
+#pragma unroll
+        for (int j = 1; j < 8; j++) v[j] = cmul_conj(v[j], tw1[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) xs[j * XSTR + lane] = v[j];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[c] = xs[k1 * XSTR + 4 * c + d];
+        __syncwarp();
+        // pass 2: DFT over c, twiddle w32^(d*p), then the 4-point DFT over d across the lane quad
+        fft8(v);
+#pragma unroll
+        for (int p = 1; p < 8; p++) v[p] = cmul_conj(v[p], s_tw2[p][d]);
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            float2 u = v[p];
+            float2 t = make_float2(__shfl_xor_sync(0xffffffffu, u.x, 2), __shfl_xor_sync(0xffffffffu, u.y, 2));
+            u = (d & 2) ? csub(t, u) : cadd(u, t);
+            if (d == 3) u = make_float2(u.y, -u.x);      // * (-i)
+            t = make_float2(__shfl_xor_sync(0xffffffffu, u.x, 1), __shfl_xor_sync(0xffffffffu, u.y, 1));
+            u = (d & 1) ? csub(t, u) : cadd(u, t);
+            // Z[k], k = k1 + 8 p + 64 q
+            const int k = k1 + 8 * p + 64 * q;
+            xs[k + 4 * (k >> 6)] = u;
+        }
+        __syncwarp();
+        // split: X[k] = (Zk + conj Zm)/2 + e^{-2 pi i k/512} (Zk - conj Zm)/(2i), m = 256 - k; P = |X|^2; floored ln
+        // (Wav2LogSpec_be.c:469-479)
+        float *dst = a.out + f * LPS_BINS;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int k = lane + 32 * j;
+            if (k <= N / 2) {
+                const int kk = k & 255, mm = (256 - k) & 255;
+                const float2 zk = xs[kk + 4 * (kk >> 6)], zm = xs[mm + 4 * (mm >> 6)];
+                const float2 A = make_float2(zk.x + zm.x, zk.y - zm.y);       // Zk + conj(Zm)
+                const float2 B = make_float2(zk.x - zm.x, zk.y + zm.y);       // Zk - conj(Zm)
+                const float2 w = s_post[k];                                    // (cos, sin)
+                // -i B = (B.y, -B.x); times (c - i s)
+                const float xr = A.x + fmaf(B.y, w.x, -B.x * w.y);
+                const float xi = A.y - fmaf(B.x, w.x, B.y * w.y);
+                const float pw = 0.25f * fmaf(xr, xr, xi * xi);
+                float val = (pw < floor_fb) ? -50.0f : __logf(pw);
+                if (a.flags & LPS_FLAG_ZSCORE) val = __fmul_rn(__fsub_rn(val, a.mean[k]), a.dvar[k]);   // Interface.cc:763-764
+                if (a.flags & LPS_FLAG_BIG_ENDIAN) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
+                dst[k] = val;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+void build_fast_tab(FastTab &T)
+{
+    const double PI = 3.14159265358979323846;
+    for (int i = 0; i < N; i++) {
+        const int p = i < N / 2 ? i : N - 1 - i;          // the reference applies win[i] to both ends (FEfunc.c:106-118)
+        T.win[i] = (float)(0.54 - 0.46 * cos(6.28318530717958647692 * p / (N - 1)));
+    }
+    for (int k = 0; k < 8; k++)
+        for (int b = 0; b < 32; b++) T.tw1[k][b] = make_float2((float)cos(2 * PI * b * k / 256), (float)sin(2 * PI * b * k / 256));
+    for (int p = 0; p < 8; p++)
+        for (int d = 0; d < 4; d++) T.tw2[p][d] = make_float2((float)cos(2 * PI * d * p / 32), (float)sin(2 * PI * d * p / 32));
+    for (int k = 0; k < LPS_BINS; k++) T.post[k] = make_float2((float)cos(2 * PI * k / 512), (float)sin(2 * PI * k / 512));
+    T.floor_fb = (float)exp((double)-50.0);
 }
 
 }  // namespace

@@ -229,6 +229,7 @@ def test_reused_host_buffer_growing_chunks(pkg, oracle):
     W, b, x, t = make_case(O, layersizes, M * 150, 41)     # 300*4*128*150 = 23 MB: above the 1 MB pinning threshold
     buf_x = np.zeros_like(x); buf_t = np.zeros_like(t)
     net = pkg.BP_GPU(0, 0, 3, layersizes, M, 0.05, 0.9, 1e-5, W, b, 1.5, 1, flags=pkg.FLAG_PIN_HOST)
+    net.keep_pinned(buf_x, buf_t)                            # long-lived: the registration survives across calls
     orc = O.OracleNet(layersizes, M, 0.05, 0.9, 1e-5, 1.5, 1, W, b)
     pos = 0
     for nb in (20, 130):                                    # small chunk first, then a much larger one in the same buffer
@@ -242,3 +243,69 @@ def test_reused_host_buffer_growing_chunks(pkg, oracle):
     Wo, _ = orc.weights()
     for l in range(2):
         assert rel_err(Wg[l], Wo[l]) < 1e-3
+
+
+@pytest.mark.parametrize("M", [256, 512, 1024, 200])
+@pytest.mark.parametrize("MLflag,beta", [(1, 1.5), (0, 2.0)])
+def test_wide_bunch_sizes(pkg, oracle, M, MLflag, beta):
+    """bunches above 128 frames: forward / backward over several row tiles, stand-alone loss kernel, and the WIDE persistent
+    gradient+update kernel (dw_wide.cu: frames streamed in 32-frame blocks, 64..256-unit segments) + bias_wide_kernel,
+    over several steps against the oracle (BP_GPU.cu:170-184 for any bunch size)"""
+    O = oracle
+    layersizes, nb = [7 * 33, 200, 330, 33], 4     # ragged: Kp = 256 / 256 / 384 (segments of 4 and 2 slabs), Np = 256 / 384 / 64
+    W, b, x, t = make_case(O, layersizes, M * nb, 23)
+    orc = O.OracleNet(layersizes, M, 0.1, 0.9, 1e-5, beta, MLflag, W, b)
+    net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, 0.1, 0.9, 1e-5, W, b, beta, MLflag)
+    lo, al = orc.train(x, t)
+    net.train(x.shape[0], x, t)
+    assert np.max(np.abs(net.losses() - lo) / np.abs(lo)) < 5e-3
+    if MLflag == 1:
+        assert rel_err(net.alpha(), al[-1]) < 1e-3
+    Wg, bg = net.returnWeights()
+    Wo, bo = orc.weights()
+    for l in range(len(layersizes) - 1):
+        assert rel_err(Wg[l], Wo[l]) < 1e-3
+        assert rel_err(Wg[l] - W[l], Wo[l] - W[l]) < 2e-3, "update of layer %d" % (l + 1)
+        assert rel_err(bg[l], bo[l]) < 2e-3
+    net.close()
+
+
+def test_wide_kernel_at_128_equals_persist(pkg, oracle, monkeypatch):
+    """GGD_DW_PERSIST=0 routes a 128-frame bunch through dw_wide.cu: same weights as dw_persist.cu (same products, fp32
+    accumulation in a different order)"""
+    O = oracle
+    layersizes, M, nb = [7 * 33, 200, 130, 33], 128, 6
+    W, b, x, t = make_case(O, layersizes, M * nb, 29)
+    res = []
+    for env in ("1", "0"):
+        monkeypatch.setenv("GGD_DW_PERSIST", env)
+        net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1)
+        net.train(x.shape[0], x, t)
+        res.append((net.returnWeights(), net.alpha(), net.losses()))
+        net.close()
+    (Wa, ba), aa, la = res[0]
+    (Wb, bb), ab, lb = res[1]
+    for u, v in zip(Wa + ba, Wb + bb):
+        assert rel_err(u, v) < 1e-5
+    assert rel_err(aa, ab) < 1e-5 and np.allclose(la, lb, rtol=1e-5)
+
+
+@pytest.mark.parametrize("M", [1024, 256])
+def test_config4_shape_single_gpu(pkg, oracle, M):
+    """BASELINE config 4's network (ctx 11: 2827-2048^3-257) on ONE GPU with the whole global minibatch, against the oracle"""
+    O = oracle
+    layersizes = [2827, 2048, 2048, 2048, 257]
+    W, b, x, t = make_case(O, layersizes, 2 * M, 31)
+    orc = O.OracleNet(layersizes, M, 0.1, 0.9, 1e-5, 1.5, 1, W, b)
+    net = pkg.BP_GPU(0, 0, 5, layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1)
+    lo, al = orc.train(x, t)
+    net.train(x.shape[0], x, t)
+    assert np.max(np.abs(net.losses() - lo) / np.abs(lo)) < 5e-3
+    assert rel_err(net.alpha(), al[-1]) < 1e-3
+    Wg, bg = net.returnWeights()
+    Wo, bo = orc.weights()
+    for l in range(4):
+        assert rel_err(Wg[l], Wo[l]) < 1e-3
+        assert rel_err(Wg[l] - W[l], Wo[l] - W[l]) < 2e-3, "update of layer %d" % (l + 1)
+        assert rel_err(bg[l] - b[l], bo[l] - b[l]) < 2e-3
+    net.close()
