@@ -5,9 +5,10 @@
  *  fileio.c:231-243, 268-282): int16 PCM -> 512-sample frames every 256 samples -> Hamming window ->
  * 512-point real split-radix FFT -> power -> floored natural log -> 257 bins per frame.
  *
- * The kernel executes the reference's butterfly network itself (same operations, same order within each
- * butterfly, no FMA contraction), so features are bit-identical to the reference except where the
- * double-precision log of the GPU differs from glibc's in the last place.
+ * Two kernels: the default computes the same transform with a register-resident radix-8 FFT (throughput path: fp32,
+ * exactly rounded twiddles); with LPS_FLAG_EXACT the kernel executes the reference's butterfly network itself (same
+ * operations, same order within each butterfly, no FMA contraction), so features are bit-identical to the reference
+ * except where the double-precision log of the GPU differs from glibc's in the last place.
  *
  * Entry point               replaces
  * ------------------------  ---------------------------------------------------------------------
@@ -32,7 +33,10 @@ extern "C" {
 
 enum {
     LPS_FLAG_BIG_ENDIAN = 1,  /* byte-swap each float (ready for fwrite into an HTK file) */
-    LPS_FLAG_ZSCORE = 2       /* (x - mean[k]) * dvar[k] with the .norm constants; not combinable with BIG_ENDIAN */
+    LPS_FLAG_ZSCORE = 2,      /* (x - mean[k]) * dvar[k] with the .norm constants; not combinable with BIG_ENDIAN */
+    LPS_FLAG_EXACT = 4        /* execute the reference's split-radix butterfly network itself (bit-identical spectrum, HTK-identical
+                                 files) instead of the default register-resident radix-8 FFT (fp32; agrees with the reference to
+                                 ~1e-6 of the feature range, see tests/test_lps_gpu.py) */
 };
 
 typedef struct lps_handle lps_handle;

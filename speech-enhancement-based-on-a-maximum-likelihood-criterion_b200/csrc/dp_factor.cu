@@ -10,10 +10,17 @@ __device__ __forceinline__ void st_na_v4(void *p, uint4 v)
     asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(256) factor_push_kernel(const FxPushArgs a)
 {
-    __shared__ int s_last;
     const unsigned int step = *a.step_counter + 1u;
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[a.event * 4 + 0] = gtime();
     if (a.wait_done) {
         // every peer must have finished step-1 (it no longer reads the arena slices this step overwrites)
         if (threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
@@ -30,6 +37,7 @@ __global__ void __launch_bounds__(256) factor_push_kernel(const FxPushArgs a)
         }
         __syncthreads();
     }
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[a.event * 4 + 1] = gtime();
     const long long bunch = a.ctl->bunch_idx;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int sg = 0; sg < a.nseg; sg++) {
@@ -54,17 +62,19 @@ __global__ void __launch_bounds__(256) factor_push_kernel(const FxPushArgs a)
             }
         }
     }
-    // flag: once EVERY block's stores are performed system-wide, tell all peers
-    __threadfence_system();
+    // flag: once EVERY block's stores are performed system-wide, tell all peers.  One fence per block: the barrier orders
+    // the block's stores before thread 0's system-scope fence (cumulativity), 24 000 concurrent membar.sys cost ~15 us
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int prev = atomicAdd(a.block_counter, 1u);
-        s_last = (prev == gridDim.x - 1);
-        if (s_last) {
+        if (prev == gridDim.x - 1) {
             *a.block_counter = 0;
             __threadfence_system();
+            if (a.trace) a.trace[a.event * 4 + 2] = gtime();
             for (int p = 0; p < a.world; p++)
                 if (p != a.rank) st_release_sys_u32(a.peer_flags[p] + a.rank * FX_STRIDE + a.event, step);
+            if (a.trace) a.trace[a.event * 4 + 3] = gtime();
         }
     }
 }
@@ -83,6 +93,7 @@ __global__ void __launch_bounds__(BW_COLS *BW_ROWL) bias_wide_kernel(const BiasW
     const int tx = threadIdx.x % BW_COLS, ty = threadIdx.x / BW_COLS;
     const int n = blockIdx.x * BW_COLS + tx;
     const bool active = blockIdx.x * BW_COLS < L.N;
+    if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.trace[FX_TRACE_BIAS] = gtime();
     if (active && a.world > 1 && L.ev_dx >= 0) {
         const unsigned int step = *a.bias_step + 1u;
         if (threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
@@ -123,6 +134,7 @@ __global__ void __launch_bounds__(BW_COLS *BW_ROWL) bias_wide_kernel(const BiasW
         if (prev == total - 1) {
             *a.block_counter = 0;
             *a.bias_step += 1u;
+            if (a.trace) a.trace[FX_TRACE_BIAS + 1] = gtime();
         }
     }
 }

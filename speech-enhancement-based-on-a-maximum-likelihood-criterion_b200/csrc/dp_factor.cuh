@@ -23,6 +23,8 @@
 
 namespace ggd {
 
+constexpr int FX_TRACE_WIDE = 4 * FX_STRIDE, FX_TRACE_BIAS = FX_TRACE_WIDE + 16, FX_TRACE_WORDS = FX_TRACE_BIAS + 4;
+
 struct FxSeg {
     const uint8_t *src;          // local source (my slice)
     long long src_bunch_stride;  // bytes added per ctl->bunch_idx (the net-input rows live in the chunk arrays), else 0
@@ -44,6 +46,7 @@ struct FxPushArgs {
     int event;                            // FX_EV_Y + l or FX_EV_DX + l
     int wait_done;                        // first push of a step: wait until every peer has finished the previous step
     int include_self;                     // also copy into my own arena (net-input rows)
+    unsigned long long *trace;            // optional globaltimer stamps [event*4 + {start, waited, copied, flagged}] (GGD_FX_TRACE=1)
 };
 void launch_factor_push(const FxPushArgs &a, int grid, cudaStream_t s);
 
@@ -64,6 +67,7 @@ struct BiasWideArgs {
     unsigned int *block_counter;
     unsigned int *error_flag;
     unsigned int *hang;
+    unsigned long long *trace;   // optional: [FX_TRACE_BIAS + {start, end}]
 };
 void launch_bias_wide(const BiasWideArgs &a, cudaStream_t s);
 

@@ -8,8 +8,8 @@
 //
 //     g[n][k] = sum_m dx[m][n] * y[m][k]      UMMA: M = 128 (n, TMEM lanes), N = 64..256 (k, TMEM columns), K = frames
 //
-// Work unit: a SLAB = 128 output units n x 64 input units k of one weight matrix.  The global slab list (layer, n-tile,
-// k-slab; k fastest) is cut into gridDim.x contiguous ranges (balanced to one slab); inside its range a CTA forms
+// Work unit: a SLAB = 128 output units n x 64 input units k of one weight matrix.  Every layer's slab list (n-tile, k-slab;
+// k fastest) is cut into gridDim.x contiguous ranges (balanced to one slab); inside its range a CTA forms
 // SEGMENTS of up to 4 consecutive slabs of one n-tile (UMMA N = 64 w <= 256), so that the dx^T operand is re-read once
 // per 256 input units instead of once per 64: L2 -> SM operand traffic per weight drops 2.4x against 128 x 64 tiles.
 // The frames are streamed in blocks of 32 through a TMA ring (48 KB per stage: dx^T 128 n x 32 frames hi+lo, y^T
@@ -25,7 +25,7 @@
 //   warp 11     weight producer: fp32 W and delta quarter tiles by TMA, running ahead of the update by the ring depth
 // All global traffic is TMA.  HBM bytes: 16 B/param (read W, delta; write W, delta).  The bias gradients + bias update
 // are a separate small kernel on a second stream (dp_factor.cu: bias_wide_kernel).
-#include "dw_wide.cuh"
+#include "dp_factor.cuh"
 #include "pipe.cuh"
 #include "../../include/ggd_train.h"
 #include <stdlib.h>
@@ -52,21 +52,31 @@ struct WSeg {
     int li, nt, ks, w;
 };
 
-__device__ __forceinline__ WSeg wide_seg(const DwwArgs *gp, int s, int s1)
-{
-    int l = 0;
-#pragma unroll 1
-    while (l + 1 < gp->nlayers && s >= gp->layer[l + 1].slab_base) l++;
-    const DwwLayer *L = &gp->layer[l];
-    const int r = s - L->slab_base;
-    WSeg g;
-    g.L = L; g.li = l; g.nt = r / L->k_slabs; g.ks = r - g.nt * L->k_slabs;
-    int w = L->k_slabs - g.ks;
-    if (w > dww::MAXW) w = dww::MAXW;
-    if (w > s1 - s) w = s1 - s;
-    g.w = w;
-    return g;
-}
+// Every CTA takes the same share of EVERY layer (a contiguous sub-range of the layer's slabs), walking the layers in list
+// order: in data-parallel mode the factors of the top layers arrive first, so nobody idles waiting for the bottom layer.
+struct SegIter {
+    const DwwArgs *gp;
+    int li, s, s1;
+    __device__ __forceinline__ explicit SegIter(const DwwArgs *g) : gp(g), li(-1), s(0), s1(0) {}
+    __device__ __forceinline__ bool next(WSeg &g)
+    {
+        while (s >= s1) {
+            if (++li >= gp->nlayers) return false;
+            const DwwLayer *L = &gp->layer[li];
+            s = L->slab_base + (int)((long long)L->n_slabs * blockIdx.x / gridDim.x);
+            s1 = L->slab_base + (int)((long long)L->n_slabs * (blockIdx.x + 1) / gridDim.x);
+        }
+        const DwwLayer *L = &gp->layer[li];
+        const int r = s - L->slab_base;
+        g.L = L; g.li = li; g.nt = r / L->k_slabs; g.ks = r - g.nt * L->k_slabs;
+        int w = L->k_slabs - g.ks;
+        if (w > dww::MAXW) w = dww::MAXW;
+        if (w > s1 - s) w = s1 - s;
+        g.w = w;
+        s += w;
+        return true;
+    }
+};
 
 // bounded wait for the factor flags `ev` of every peer (value >= step); a lost peer must not hang the GPU
 __device__ __noinline__ void wide_wait_flags(const DwwArgs *gp, int ev, unsigned int step)
@@ -99,8 +109,6 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = gp->total_slabs;
-    const int s0 = (int)((long long)T * blockIdx.x / gridDim.x), s1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
     const int FB = gp->fblocks;
     unsigned int *const hang = gp->hang;
 
@@ -118,22 +126,29 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    pdl_wait();   // the factors of this step are complete and visible from here on
-    const int bunch_row0 = gp->ctl->bunch_idx * gp->rows_per_bunch;
+    if (gp->trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gp->trace[FX_TRACE_WIDE] = t; }
+    // The weight producer does NOT wait for the previous kernel: W and delta are only read by the chain, and nothing is stored
+    // before the MMAs (which need the factors, i.e. griddepcontrol.wait) have finished -- the HBM stream is primed while the
+    // last GEMM of the backward chain drains.
+    if (warp != 11) pdl_wait();   // the factors of this step are complete and visible from here on
+    if (gp->trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gp->trace[FX_TRACE_WIDE + 1] = t; }
+    const int bunch_row0 = (warp == 11) ? 0 : gp->ctl->bunch_idx * gp->rows_per_bunch;
 
     if (warp == 0) {
-        if (lane == 0 && s0 < s1) {
+        if (lane == 0) {
             // ===== operand producer =====
             const unsigned int step = gp->world > 1 ? *gp->step_counter + 1u : 0u;
             int st = 0, ph = 0, ready = -1, it = 0;
-            for (int s = s0; s < s1;) {
-                const WSeg g = wide_seg(gp, s, s1);
+            SegIter si(gp);
+            WSeg g;
+            while (si.next(g)) {
                 const DwwLayer *L = g.L;
                 if (gp->world > 1 && g.li != ready) {
                     wide_wait_flags(gp, L->ev_dx, step);
                     wide_wait_flags(gp, L->ev_y, step);
                     asm volatile("fence.proxy.async;" ::: "memory");   // peer (generic-proxy) writes -> my TMA reads
                     ready = g.li;
+                    if (gp->trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(gp->trace + FX_TRACE_WIDE + 2 + g.li, t); }
                 }
                 const int r0 = L->b_rows_from_ctl ? bunch_row0 : 0;
                 const uint32_t bytes = 2 * A_PART + 2 * g.w * BOX;
@@ -152,16 +167,16 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
                     }
                     if (++st == OPS) { st = 0; ph ^= 1; }
                 }
-                s += g.w;
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && s0 < s1) {
+        if (lane == 0) {
             // ===== MMA issuer =====
             int st = 0, ph = 0, it = 0, seg_it = 0;
-            for (int s = s0; s < s1; seg_it++) {
-                const WSeg g = wide_seg(gp, s, s1);
+            SegIter si(gp);
+            WSeg g;
+            for (; si.next(g); seg_it++) {
                 const int acc = seg_it & 1;
                 mbar_wait_bounded(&t_empty[acc], ((seg_it >> 1) & 1) ^ 1, hang, 6, seg_it);
                 tc_fence_after();
@@ -185,17 +200,17 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
                     if (++st == OPS) { st = 0; ph ^= 1; }
                 }
                 umma_commit(&t_full[acc]);
-                s += g.w;
             }
         }
         __syncwarp();
     } else if (warp == 10) {
-        if (lane == 0 && s0 < s1) {
+        if (lane == 0) {
             // ===== store warp =====
             const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
             int ws = 0, wph = 0, prev_ws = -1, it = 0;
-            for (int s = s0; s < s1;) {
-                const WSeg g = wide_seg(gp, s, s1);
+            SegIter si(gp);
+            WSeg g;
+            while (si.next(g)) {
                 const DwwLayer *L = g.L;
                 const int nq = 4 * g.w;
                 for (int qt = 0; qt < nq; qt++, it++) {
@@ -218,18 +233,18 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
                     prev_ws = ws;
                     if (++ws == WDS) { ws = 0; wph ^= 1; }
                 }
-                s += g.w;
             }
             tma_store_wait_all<0>();   // all writes performed before the CTA (and with it the grid) completes
         }
         __syncwarp();
     } else if (warp == 11) {
-        if (lane == 0 && s0 < s1) {
+        if (lane == 0) {
             // ===== weight producer: W and delta quarter tiles, ahead of the update by the ring depth =====
             const uint64_t pol_stream = l2_policy_evict_first();
             int ws = 0, wph = 0, it = 0;
-            for (int s = s0; s < s1;) {
-                const WSeg g = wide_seg(gp, s, s1);
+            SegIter si(gp);
+            WSeg g;
+            while (si.next(g)) {
                 const DwwLayer *L = g.L;
                 const int nq = 4 * g.w;
                 for (int qt = 0; qt < nq; qt++, it++) {
@@ -246,17 +261,17 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
                     }
                     if (++ws == WDS) { ws = 0; wph ^= 1; }
                 }
-                s += g.w;
             }
         }
         __syncwarp();
-    } else if (s0 < s1) {
+    } else {
         // ===== update warps (8): quadrant q = accumulator lanes [32q, 32q+32); `h` = which 8 of a stage's 16 rows =====
         const int e = warp - 2, q = warp & 3, h = e >> 2;
         const float mom = gp->mom, lr = gp->lr, inv_mg = 1.0f / gp->Mg;
         int ws = 0, wph = 0, it = 0, seg_it = 0;
-        for (int s = s0; s < s1; seg_it++) {
-            const WSeg g = wide_seg(gp, s, s1);
+        SegIter si(gp);
+        WSeg g;
+        for (; si.next(g); seg_it++) {
             const float wc = g.L->wc;
             const int acc = seg_it & 1;
             mbar_wait_bounded(&t_full[acc], (seg_it >> 1) & 1, hang, 8, seg_it);
@@ -290,7 +305,6 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
                 if (lane == 0) mbar_arrive(&wd_done[ws]);
                 if (++ws == WDS) { ws = 0; wph ^= 1; }
             }
-            s += g.w;
         }
     }
     pdl_trigger();
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
         if (prev == gridDim.x - 1) {
             *gp->done_counter = 0;
             gp->ctl->bunch_idx += 1;
+            if (gp->trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); gp->trace[FX_TRACE_WIDE + 14] = t; }
             if (gp->world > 1) {
                 const unsigned int step = *gp->step_counter + 1u;
                 *gp->step_counter = step;

@@ -13,6 +13,7 @@ struct DwwLayer {
     int Kp, Np;
     int k_slabs;              // Kp / 64
     int slab_base;            // index of this layer's first slab in the global list
+    int n_slabs;              // slabs of this layer: ceil(Np / 128) * k_slabs
     int b_rows_from_ctl;      // add ctl->bunch_idx * rows_per_bunch to the frame coordinate of b_hi / b_lo (one GPU, layer 1)
     int ev_dx, ev_y;          // data parallel: flags that every peer must have raised before the operands are read (-1: none)
     float wc;
@@ -35,6 +36,7 @@ struct DwwArgs {
     unsigned int *peer_flags[FX_MAX];     // every rank's flag block
     unsigned int *step_counter;           // completed data-parallel steps
     unsigned int *error_flag;
+    unsigned long long *trace;            // optional: [FX_TRACE_WIDE + {start, flags of list layer 0..9 seen, end}] (block 0 / last block)
 };
 int dw_wide_smem(int fblocks, int *op_stages, int *wd_stages);
 int launch_dw_wide(const DwwArgs *dev_args, int grid, int smem_bytes, cudaStream_t s);

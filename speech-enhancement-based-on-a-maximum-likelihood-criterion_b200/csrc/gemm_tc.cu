@@ -186,8 +186,8 @@ __device__ __forceinline__ void epilogue_loss16(const GemmArgs &g, int i, int j,
         float s = 0.0f;
 #pragma unroll 1
         for (int q = 0; q < 8; q++) s += part[q][t];
-        if (g.world > 1 && g.ml) {
-            // frame-sharded data parallelism: alpha needs the sum over the GLOBAL minibatch
+        if (g.world > 1) {
+            // frame-sharded data parallelism: alpha (and the loss trace) need the sum over the GLOBAL minibatch
             const unsigned int step = *g.step_counter + 1u;
             const int chunk = j >> 4;
             if (live)

@@ -19,6 +19,7 @@
 #include <string.h>
 #include <math.h>
 #include <vector>
+#include <string>
 #include <map>
 #include <algorithm>
 
@@ -50,7 +51,8 @@ using namespace ggd;
     } while (0)
 
 constexpr int HANG_WORDS = 8 + 160 * 12 * 4;
-constexpr int FX_NEVENTS = 24;      // fork / join events of one step
+constexpr int FX_NEVENTS = 64;      // fork / join events of one step
+constexpr int FX_NSIDE = 12;        // side streams: every factor push (and the bias update) is its own branch of the step graph
 // fx_counters words
 constexpr int FXC_STEP = 0, FXC_BIAS_STEP = 1, FXC_BIAS_BLOCKS = 2, FXC_ERROR = 3, FXC_PUSH_BLOCKS = 8, FXC_WORDS = 8 + FX_STRIDE;
 
@@ -91,7 +93,7 @@ struct ggd_handle {
     bf16 *c_hi, *c_lo;
     size_t cap;         // frames
     std::map<const void *, size_t> pinned;
-    cudaStream_t s_main, s_comm, s_copy;
+    cudaStream_t s_main, s_side[FX_NSIDE], s_copy;
     std::vector<cudaEvent_t> ev_piece;   // upload pipeline: piece p of the chunk has landed
     cudaEvent_t ev_c0, ev_c1;
     cudaEvent_t ev0, ev1, ev2;
@@ -125,6 +127,7 @@ struct ggd_handle {
     void *fx_peer[3][FX_MAX];       // IPC-mapped: factor arena, asum, flags of every rank
     FxPushArgs fx_push[FX_STRIDE];  // by event (FX_EV_Y + l, FX_EV_DX + l)
     int fx_push_ctas;
+    unsigned long long *fx_trace;   // GGD_FX_TRACE=1: globaltimer stamps of the last step's pushes / wide / bias kernels
     // host mirrors / stats
     std::vector<float> losses;
     std::vector<float> h_out;
@@ -269,7 +272,7 @@ static int build_plans(ggd_handle *h)
         // the weights are written by the update kernel(s) at the END of a step; only the first forward launch follows them directly
         h->fwd[l].args.b_early = (l != 1); h->dxp[l].args.b_early = 1;
     }
-    { const char *ev = getenv("GGD_WIDE_PDL"); h->fwd[1].no_pdl = h->wide && !(ev && atoi(ev) == 1); }   // fwd[1] follows the join with the side stream
+    { const char *ev = getenv("GGD_WIDE_PDL"); h->fwd[1].no_pdl = h->wide && ev && atoi(ev) == 0; }   // fwd[1] follows the join with the side streams; PDL on that edge still captures (-9 us per step)
     if (h->fuse_loss) {
         const LayerInfo &top = h->lay[L - 1];
         GemmPlan &p = h->fwd_loss;
@@ -334,7 +337,7 @@ static int build_plans(ggd_handle *h)
             if (!rc) rc = make_tmap_bf16(&d.b_lo, in_chunk ? h->c_lo : h->act_lo[l - 1], in_chunk ? (long long)h->cap : h->fx_rows, ly.Kp, ly.Kp, 32);
             if (!rc) rc = make_tmap_2d(&d.w_map, h->P + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 16, 0);
             if (!rc) rc = make_tmap_2d(&d.d_map, h->Dl + ly.w_off, 1, ly.Kp, ly.Np, ly.Np, 128, 16, 0);
-            d.Kp = ly.Kp; d.Np = ly.Np; d.k_slabs = ly.Kp / 64; d.slab_base = base;
+            d.Kp = ly.Kp; d.Np = ly.Np; d.k_slabs = ly.Kp / 64; d.slab_base = base; d.n_slabs = ceil_div(ly.Np, 128) * d.k_slabs;
             d.b_rows_from_ctl = in_chunk;
             d.ev_dx = h->dp_fx ? FX_EV_DX + l : -1; d.ev_y = h->dp_fx ? FX_EV_Y + (l - 1) : -1;
             d.wc = h->cfg.weightcost;
@@ -351,6 +354,7 @@ static int build_plans(ggd_handle *h)
             a->flags = h->fx_flags; a->step_counter = h->fx_counters + FXC_STEP; a->error_flag = h->fx_counters + FXC_ERROR;
             for (int p = 0; p < world; p++) a->peer_flags[p] = (unsigned int *)h->fx_peer[2][p];
         }
+        a->trace = h->fx_trace;
         cudaError_t e = (rc == GGD_OK) ? cudaMemcpy(h->dww_dev, a, sizeof *a, cudaMemcpyHostToDevice) : cudaSuccess;
         delete a;
         GGD_TRY(rc);
@@ -368,6 +372,7 @@ static int build_plans(ggd_handle *h)
         b.rows = h->fx_rows; b.mom = h->cfg.momentum; b.lr = h->cfg.lrate; b.Mg = (float)h->Mg;
         b.world = world; b.rank = rank; b.hang = h->hang_dev;
         b.flags = h->fx_flags;
+        b.trace = h->fx_trace;
         b.bias_step = h->fx_counters + FXC_BIAS_STEP; b.block_counter = h->fx_counters + FXC_BIAS_BLOCKS; b.error_flag = h->fx_counters + FXC_ERROR;
     }
     if (h->dp_fx) {
@@ -382,7 +387,8 @@ static int build_plans(ggd_handle *h)
             for (int q = 0; q < world; q++) { p.peer_arena[q] = (uint8_t *)h->fx_peer[0][q]; p.peer_flags[q] = (unsigned int *)h->fx_peer[2][q]; }
             p.my_flags = h->fx_flags; p.ctl = h->ctl; p.step_counter = h->fx_counters + FXC_STEP;
             p.block_counter = h->fx_counters + FXC_PUSH_BLOCKS + event; p.error_flag = h->fx_counters + FXC_ERROR; p.hang = h->hang_dev;
-            p.world = world; p.rank = rank; p.event = event; p.wait_done = first_of_step; p.include_self = first_of_step;
+            p.world = world; p.rank = rank; p.event = event; p.wait_done = 1; p.include_self = first_of_step;   // (the pushes of a step run in parallel: each checks DONE)
+            p.trace = h->fx_trace;
         };
         // the net-input rows of the current bunch live in the chunk arrays: they are copied into EVERY arena (mine included)
         make_push(FX_EV_Y + 0, h->act_hi[0], h->act_lo[0], 0, h->c_hi, h->c_lo, (long long)h->M * h->upad[0] * sizeof(bf16), 1);
@@ -458,37 +464,54 @@ static int dp_fx_setup(ggd_handle *h)
     GGD_CUDA(cudaMemset(h->fx_flags, 0, (size_t)FX_MAX * FX_STRIDE * sizeof(unsigned int)));
     void *local[3] = {h->fx_arena, h->fx_asum, h->fx_flags};
     GGD_TRY(ipc_exchange(h, local, 3, h->fx_peer));
-    { const char *ev = getenv("GGD_FX_PUSH_CTAS"); h->fx_push_ctas = (ev && atoi(ev) > 0) ? atoi(ev) : 96; }
+    { const char *ev = getenv("GGD_FX_PUSH_CTAS"); h->fx_push_ctas = (ev && atoi(ev) > 0) ? atoi(ev) : 32 + 16 * (world - 2); }   // 32 CTAs per peer-MB is ample
     GGD_TRY(dp_barrier(h));    // nobody may enter the first step before every rank has mapped everyone
     return GGD_OK;
 }
 
 // ---- one training step (forward, loss gradient, backward, update); stream-ordered, no host sync ----
-// side stream: waits for everything queued on `s` so far
-static int fx_fork(ggd_handle *h, cudaStream_t s, int *nfork)
+// Side branches of a step.  Every factor push (and the bias update) runs on its OWN side stream, forked from the compute
+// stream right after its producer: in the captured graph these are parallel branches, so neither the launch gaps nor the
+// NVLink round trips of one push delay the next one (8 pushes in a row on one stream took 125 us against a 75 us chain).
+struct SideCtx { int nfork, nside; };
+static int fx_fork(ggd_handle *h, cudaStream_t s, SideCtx *sc, cudaStream_t *side)
 {
-    cudaEvent_t e = h->ev_fx[(*nfork)++ % FX_NEVENTS];
+    cudaEvent_t e = h->ev_fx[sc->nfork++ % FX_NEVENTS];
+    *side = h->s_side[sc->nside++ % FX_NSIDE];
     GGD_CUDA(cudaEventRecord(e, s));
-    GGD_CUDA(cudaStreamWaitEvent(h->s_comm, e, 0));
+    GGD_CUDA(cudaStreamWaitEvent(*side, e, 0));
     return GGD_OK;
 }
-// factor push of one array on the side stream, after everything queued on `s` so far
-static int fx_push(ggd_handle *h, cudaStream_t s, int event, int *nfork, int *launches)
+// all side branches of this step join the compute stream
+static int fx_join(ggd_handle *h, cudaStream_t s, SideCtx *sc)
 {
-    GGD_TRY(fx_fork(h, s, nfork));
-    ProfScope ps(h, KC_PUSH, h->s_comm);
-    launch_factor_push(h->fx_push[event], h->fx_push_ctas, h->s_comm); (*launches)++;
+    const int used = sc->nside < FX_NSIDE ? sc->nside : FX_NSIDE;
+    for (int i = 0; i < used; i++) {
+        cudaEvent_t e = h->ev_fx[sc->nfork++ % FX_NEVENTS];
+        GGD_CUDA(cudaEventRecord(e, h->s_side[i]));
+        GGD_CUDA(cudaStreamWaitEvent(s, e, 0));
+    }
+    sc->nside = 0;
+    return GGD_OK;
+}
+// factor push of one array on a side stream, after everything queued on `s` so far
+static int fx_push(ggd_handle *h, cudaStream_t s, int event, SideCtx *sc, int *launches)
+{
+    cudaStream_t side;
+    GGD_TRY(fx_fork(h, s, sc, &side));
+    ProfScope ps(h, KC_PUSH, side);
+    launch_factor_push(h->fx_push[event], h->fx_push_ctas, side); (*launches)++;
     return GGD_OK;
 }
 
-static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches, bool train = false, bool fx = false, int *nfork = nullptr)
+static int enqueue_forward(ggd_handle *h, cudaStream_t s, int *launches, bool train = false, bool fx = false, SideCtx *sc = nullptr)
 {
     const int L = h->L;
     if (h->tensor) {
         for (int l = 1; l < L; l++) {
             { ProfScope ps(h, KC_FWD, s);
               GGD_TRY(launch_gemm_tc((train && h->fuse_loss && l == L - 1) ? h->fwd_loss : h->fwd[l], s)); (*launches)++; }
-            if (fx && l < L - 1) GGD_TRY(fx_push(h, s, FX_EV_Y + l, nfork, launches));
+            if (fx && l < L - 1) GGD_TRY(fx_push(h, s, FX_EV_Y + l, sc, launches));
         }
     } else {
         launch_simt_gather_in(h->ctl, h->M, h->units[0], h->y32[0], h->upad[0], s); (*launches)++;
@@ -508,10 +531,10 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     const bool fx = h->dp_fx && fused;      // factor exchange: pushes on the side stream, replicated update
     const int L = h->L;
     const LayerInfo &top = h->lay[L - 1];
-    int nfork = 0;
+    SideCtx sc = {0, 0};
     if (h->dp_fx && !fused) { set_error("data-parallel steps need the fused update path"); return GGD_EUNSUPPORTED; }
-    if (fx) GGD_TRY(fx_push(h, s, FX_EV_Y + 0, &nfork, launches));    // net-input rows of this bunch -> every arena
-    GGD_TRY(enqueue_forward(h, s, launches, true, fx, &nfork));
+    if (fx) GGD_TRY(fx_push(h, s, FX_EV_Y + 0, &sc, launches));    // net-input rows of this bunch -> every arena
+    GGD_TRY(enqueue_forward(h, s, launches, true, fx, &sc));
     // ---- fused loss gradient (BP_GPU.cu:408-424); with fuse_loss it already ran in the output layer's epilogue
     LossArgs la;
     memset(&la, 0, sizeof la);
@@ -521,14 +544,14 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     la.dx_hi = h->tensor ? loc(h, h->dx_hi[L - 1], L - 1) : nullptr; la.dx_lo = h->tensor ? loc(h, h->dx_lo[L - 1], L - 1) : nullptr;
     la.ldx = top.Np; la.alpha = h->alpha; la.colsum = h->colsum; la.trace = h->trace;
     if (h->fuse_loss) {
-    } else if (h->fx_loss && la.ml) {
+    } else if (h->fx_loss) {
         // partial sum|e|^beta exchanged over peer memory inside the loss kernel (no NCCL on the step)
         ProfScope ps(h, KC_LOSS, s);
         la.mode = 3; la.world = h->cfg.world_size; la.rank = h->cfg.rank;
         la.step_counter = h->fx_counters + FXC_STEP; la.error_flag = h->fx_counters + FXC_ERROR;
         for (int p = 0; p < la.world; p++) { la.asum_slot[p] = (float *)h->fx_peer[1][p]; la.lflags[p] = (unsigned int *)h->fx_peer[2][p]; }
         launch_loss(la, s); (*launches)++;
-    } else if (h->has_comm && la.ml) {
+    } else if (h->has_comm) {
         { ProfScope ps(h, KC_LOSS, s); la.mode = 1; launch_loss(la, s); }
         { ProfScope ps(h, KC_ALLREDUCE, s); GGD_NCCL(ncclAllReduce(h->colsum, h->colsum, top.cur, ncclFloat, ncclSum, h->comm, s)); }
         { ProfScope ps(h, KC_LOSS, s); la.mode = 2; launch_loss(la, s); }
@@ -537,14 +560,14 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         ProfScope ps(h, KC_LOSS, s);
         la.mode = 0; launch_loss(la, s); (*launches)++;
     }
-    if (fx) GGD_TRY(fx_push(h, s, FX_EV_DX + (L - 1), &nfork, launches));
+    if (fx) GGD_TRY(fx_push(h, s, FX_EV_DX + (L - 1), &sc, launches));
     // ---- backward (BP_GPU.cu:371-438); every GEMM of the step sees the pre-update weights
     for (int l = L - 1; l > 0; l--) {
         const LayerInfo &ly = h->lay[l];
         if (h->tensor) {
             if (l != 1) {
                 { ProfScope ps(h, KC_DX, s); GGD_TRY(launch_gemm_tc(h->dxp[l], s)); (*launches)++; }
-                if (fx) GGD_TRY(fx_push(h, s, FX_EV_DX + (l - 1), &nfork, launches));
+                if (fx) GGD_TRY(fx_push(h, s, FX_EV_DX + (l - 1), &sc, launches));
             }
             if (!fused) { ProfScope ps(h, KC_DW, s); GGD_TRY(launch_gemm_tc(h->dwp[l], s)); (*launches)++; }
             // fused: all layers in one persistent launch after the backward chain
@@ -567,12 +590,11 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
     }
     if (fused && h->wide) {
         // biases on the side stream (small, latency-bound) beside the persistent weight kernel; both close the step
-        GGD_TRY(fx_fork(h, s, &nfork));
-        { ProfScope ps(h, KC_BIAS, h->s_comm); launch_bias_wide(h->bias_wide, h->s_comm); (*launches)++; }
+        cudaStream_t side;
+        GGD_TRY(fx_fork(h, s, &sc, &side));
+        { ProfScope ps(h, KC_BIAS, side); launch_bias_wide(h->bias_wide, side); (*launches)++; }
         { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_wide(h->dww_dev, h->sm_count, h->wide_smem, s)); (*launches)++; }
-        cudaEvent_t e = h->ev_fx[nfork++ % FX_NEVENTS];
-        GGD_CUDA(cudaEventRecord(e, h->s_comm));
-        GGD_CUDA(cudaStreamWaitEvent(s, e, 0));
+        GGD_TRY(fx_join(h, s, &sc));
         GGD_CUDA(cudaGetLastError());
         return GGD_OK;
     }
@@ -751,6 +773,23 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     h->stats.device_ms = ms;
     for (int b = 0; b < nb; b++) h->losses[b] = (float)tr[b];
     h->stats.d2h_bytes = nb * sizeof(double);
+    if (h->fx_trace) {
+        // per-kernel globaltimer stamps of the LAST step (tuning aid, GGD_FX_TRACE=1), in us relative to the earliest stamp
+        std::vector<unsigned long long> tr(FX_TRACE_WORDS);
+        GGD_CUDA(cudaMemcpy(tr.data(), h->fx_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (unsigned long long x : tr) if (x && x < t0) t0 = x;
+        auto us = [&](int i) { return tr[i] ? (double)(tr[i] - t0) * 1e-3 : -1.0; };
+        std::string line = "[rank " + std::to_string(h->cfg.rank) + "] fx trace (us): ";
+        char buf[160];
+        for (int ev = 0; ev < FX_STRIDE; ev++)
+            if (tr[ev * 4]) { snprintf(buf, sizeof buf, "push%d[start %.1f waited %.1f copied %.1f flagged %.1f] ", ev, us(ev * 4), us(ev * 4 + 1), us(ev * 4 + 2), us(ev * 4 + 3)); line += buf; }
+        snprintf(buf, sizeof buf, "wide[start %.1f pdl %.1f", us(FX_TRACE_WIDE), us(FX_TRACE_WIDE + 1)); line += buf;
+        for (int l = 0; l < 10; l++) if (tr[FX_TRACE_WIDE + 2 + l]) { snprintf(buf, sizeof buf, " ready%d %.1f", l, us(FX_TRACE_WIDE + 2 + l)); line += buf; }
+        snprintf(buf, sizeof buf, " end %.1f] bias[start %.1f end %.1f]", us(FX_TRACE_WIDE + 14), us(FX_TRACE_BIAS), us(FX_TRACE_BIAS + 1)); line += buf;
+        fprintf(stderr, "%s\n", line.c_str());
+        GGD_CUDA(cudaMemset(h->fx_trace, 0, FX_TRACE_WORDS * 8));
+    }
     if (h->dp_fx) {
         unsigned int err = 0;
         GGD_CUDA(cudaMemcpy(&err, h->fx_counters + FXC_ERROR, sizeof err, cudaMemcpyDeviceToHost));
@@ -838,7 +877,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
     CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev_c0)); CK(cudaEventCreate(&h->ev_c1));
-    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); CK(cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi)); }
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); for (int k = 0; k < FX_NSIDE; k++) CK(cudaStreamCreateWithPriority(&h->s_side[k], cudaStreamNonBlocking, hi)); }
     for (int k = 0; k < FX_NEVENTS; k++) CK(cudaEventCreateWithFlags(&h->ev_fx[k], cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev2));
     CK(cudaMalloc(&h->P, off * sizeof(float))); CK(cudaMalloc(&h->Dl, off * sizeof(float))); CK(cudaMalloc(&h->G, (off + h->nbias) * sizeof(float)));
@@ -859,6 +898,7 @@ int ggd_create(const ggd_config *cfg, const float *const *weights, const float *
             h->dx_hi[l] = (bf16 *)(h->fx_arena + at[l][2]); h->dx_lo[l] = (bf16 *)(h->fx_arena + at[l][3]);
         }
     }
+    { const char *ev = getenv("GGD_FX_TRACE"); if (ev && atoi(ev) == 1) { CK(cudaMalloc(&h->fx_trace, FX_TRACE_WORDS * 8)); CK(cudaMemset(h->fx_trace, 0, FX_TRACE_WORDS * 8)); } }
     CK(cudaMalloc(&h->fx_counters, FXC_WORDS * sizeof(unsigned int))); CK(cudaMemset(h->fx_counters, 0, FXC_WORDS * sizeof(unsigned int)));
     for (int l = 0; l < h->L; l++) {
         const size_t n = (size_t)h->Mp * h->upad[l];
@@ -925,7 +965,7 @@ int ggd_destroy(ggd_handle *h)
     if (h->dp_fx && h->fx_peer[0][h->cfg.rank])
         for (int p = 0; p < h->cfg.world_size; p++)
             for (int k = 0; k < 3; k++) if (p != h->cfg.rank && h->fx_peer[k][p]) cudaIpcCloseMemHandle(h->fx_peer[k][p]);
-    cudaFree(h->fx_asum); cudaFree(h->fx_flags); cudaFree(h->fx_counters); cudaFree(h->fx_arena); cudaFree(h->dww_dev);
+    cudaFree(h->fx_trace); cudaFree(h->fx_asum); cudaFree(h->fx_flags); cudaFree(h->fx_counters); cudaFree(h->fx_arena); cudaFree(h->dww_dev);
     cudaFree(h->r_fea); cudaFree(h->r_targ); cudaFree(h->r_first); cudaFree(h->r_norm);
     if (h->has_comm) ncclCommDestroy(h->comm);
     cudaFree(h->P); cudaFree(h->Dl); cudaFree(h->G); cudaFree(h->Phi); cudaFree(h->Plo);
@@ -935,7 +975,7 @@ int ggd_destroy(ggd_handle *h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     for (int k = 0; k < FX_NEVENTS; k++) if (h->ev_fx[k]) cudaEventDestroy(h->ev_fx[k]);
-    if (h->s_comm) cudaStreamDestroy(h->s_comm);
+    for (int k = 0; k < FX_NSIDE; k++) if (h->s_side[k]) cudaStreamDestroy(h->s_side[k]);
     if (h->s_main) cudaStreamDestroy(h->s_main);
     delete h;
     return GGD_OK;

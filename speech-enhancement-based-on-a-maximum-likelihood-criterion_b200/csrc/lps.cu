@@ -104,7 +104,7 @@ struct LpsArgs {
     const long long *utt_sample_off;   // [n_utts + 1]
     const long long *utt_frame_off;    // [n_utts + 1]
     int n_utts;
-    long long total_frames;
+    long long frame_begin, total_frames;   // frames [frame_begin, total_frames) of the batch are processed
     float *out;
     const float *mean, *dvar;
     int flags;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32) lps_kernel(const LpsArgs a)
     float *x = xs[warp];
     const double sqrt2_d = 1.41421356237309504880;
 
-    for (long long f = (long long)blockIdx.x * WARPS + warp; f < a.total_frames; f += (long long)gridDim.x * WARPS) {
+    for (long long f = a.frame_begin + (long long)blockIdx.x * WARPS + warp; f < a.total_frames; f += (long long)gridDim.x * WARPS) {
         // utterance of this frame: largest u with frame_off[u] <= f
         int lo = 0, hi = a.n_utts;
         while (hi - lo > 1) {
@@ -262,7 +262,7 @@ struct FastArgs {
     const int16_t *pcm;
     const long long *utt_sample_off, *utt_frame_off;
     int n_utts;
-    long long total_frames;
+    long long frame_begin, total_frames;
     float *out;
     const float *mean, *dvar;
     int flags;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 2) lps_fast_kernel(const FastArgs
     const int k1 = lane >> 2, d = lane & 3;              // second-pass role of this lane
     const int q = ((d & 1) << 1) | (d >> 1);             // output index of the cross-lane radix-4 (bit-reversed d)
 
-    for (long long f = (long long)blockIdx.x * FWARPS + warp; f < a.total_frames; f += (long long)gridDim.x * FWARPS) {
+    for (long long f = a.frame_begin + (long long)blockIdx.x * FWARPS + warp; f < a.total_frames; f += (long long)gridDim.x * FWARPS) {
         int lo = 0, hi = a.n_utts;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -384,10 +384,12 @@ void build_fast_tab(FastTab &T)
 struct lps_handle {
     int gpu, sm_count;
     Schedule *d_sched;
+    FastTab *d_tab;
     float *d_mean, *d_dvar;
     bool has_norm;
-    cudaStream_t s;
+    cudaStream_t s, s2;                 // s2: second lane of the host-batch pipeline
     cudaEvent_t e0, e1;
+    std::vector<cudaEvent_t> pe;        // per-piece kernel event pairs of the host-batch pipeline
     // staging (grown on demand)
     int16_t *d_pcm; size_t pcm_cap;
     float *d_out; size_t out_cap;
@@ -423,9 +425,15 @@ int lps_create(int gpu, lps_handle **out)
     LPS_CUDA(cudaMalloc(&h->d_sched, sizeof(Schedule)));
     LPS_CUDA(cudaMemcpy(h->d_sched, S, sizeof(Schedule), cudaMemcpyHostToDevice));
     delete S;
+    FastTab *T = new FastTab();
+    build_fast_tab(*T);
+    LPS_CUDA(cudaMalloc(&h->d_tab, sizeof(FastTab)));
+    LPS_CUDA(cudaMemcpy(h->d_tab, T, sizeof(FastTab), cudaMemcpyHostToDevice));
+    delete T;
     LPS_CUDA(cudaMalloc(&h->d_mean, LPS_BINS * sizeof(float)));
     LPS_CUDA(cudaMalloc(&h->d_dvar, LPS_BINS * sizeof(float)));
     LPS_CUDA(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
+    LPS_CUDA(cudaStreamCreateWithFlags(&h->s2, cudaStreamNonBlocking));
     LPS_CUDA(cudaEventCreate(&h->e0));
     LPS_CUDA(cudaEventCreate(&h->e1));
     *out = h;
@@ -436,6 +444,9 @@ int lps_destroy(lps_handle *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->gpu);
+    for (cudaEvent_t e : h->pe) cudaEventDestroy(e);
+    if (h->s2) cudaStreamDestroy(h->s2);
+    cudaFree(h->d_tab);
     cudaFree(h->d_sched); cudaFree(h->d_mean); cudaFree(h->d_dvar); cudaFree(h->d_pcm); cudaFree(h->d_out); cudaFree(h->d_off);
     cudaEventDestroy(h->e0); cudaEventDestroy(h->e1); cudaStreamDestroy(h->s);
     delete h;
@@ -474,21 +485,46 @@ static int offsets(lps_handle *h, const long *utt_off, int n_utts, std::vector<l
     return 0;
 }
 
-static int run_kernel(lps_handle *h, const int16_t *d_pcm, int n_utts, long long total, float *d_out, int flags)
+static int check_flags(lps_handle *h, int flags)
 {
     if ((flags & LPS_FLAG_ZSCORE) && !h->has_norm) { lps_err("LPS_FLAG_ZSCORE needs lps_set_norm first"); return -1; }
     if ((flags & LPS_FLAG_ZSCORE) && (flags & LPS_FLAG_BIG_ENDIAN)) { lps_err("ZSCORE and BIG_ENDIAN cannot be combined"); return -1; }
-    LPS_CUDA(cudaEventRecord(h->e0, h->s));
-    if (total > 0) {
+    return 0;
+}
+
+// frames [f0, f1) of the batch on stream `st`
+static int launch_frames(lps_handle *h, const int16_t *d_pcm, int n_utts, long long f0, long long f1, float *d_out, int flags, cudaStream_t st)
+{
+    if (f1 <= f0) return 0;
+    const long long n = f1 - f0;
+    if (flags & LPS_FLAG_EXACT) {
         LpsArgs a;
         a.pcm = d_pcm; a.utt_sample_off = h->d_off; a.utt_frame_off = h->d_off + n_utts + 1; a.n_utts = n_utts;
-        a.total_frames = total; a.out = d_out; a.mean = h->d_mean; a.dvar = h->d_dvar; a.flags = flags; a.sched = h->d_sched;
-        long long blocks = (total + WARPS - 1) / WARPS;
+        a.frame_begin = f0; a.total_frames = f1; a.out = d_out; a.mean = h->d_mean; a.dvar = h->d_dvar; a.flags = flags; a.sched = h->d_sched;
+        long long blocks = (n + WARPS - 1) / WARPS;
         const long long cap = (long long)h->sm_count * 6;   // persistent-style grid: 6 resident CTAs per SM
         if (blocks > cap) blocks = cap;
-        lps_kernel<<<(int)blocks, WARPS * 32, 0, h->s>>>(a);
-        LPS_CUDA(cudaGetLastError());
+        lps_kernel<<<(int)blocks, WARPS * 32, 0, st>>>(a);
+    } else {
+        FastArgs a;
+        a.pcm = d_pcm; a.utt_sample_off = h->d_off; a.utt_frame_off = h->d_off + n_utts + 1; a.n_utts = n_utts;
+        a.frame_begin = f0; a.total_frames = f1; a.out = d_out; a.mean = h->d_mean; a.dvar = h->d_dvar; a.flags = flags; a.tab = h->d_tab;
+        long long blocks = (n + FWARPS - 1) / FWARPS;
+        const long long cap = (long long)h->sm_count * 8;   // 2 resident CTAs per SM, 4 rounds for balance
+        if (blocks > cap) blocks = cap;
+        lps_fast_kernel<<<(int)blocks, FWARPS * 32, 0, st>>>(a);
     }
+    LPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int run_kernel(lps_handle *h, const int16_t *d_pcm, int n_utts, long long total, float *d_out, int flags)
+{
+    int rc = check_flags(h, flags);
+    if (rc) return rc;
+    LPS_CUDA(cudaEventRecord(h->e0, h->s));
+    rc = launch_frames(h, d_pcm, n_utts, 0, total, d_out, flags, h->s);
+    if (rc) return rc;
     LPS_CUDA(cudaEventRecord(h->e1, h->s));
     return 0;
 }
@@ -528,14 +564,36 @@ int lps_extract_batch(lps_handle *h, const int16_t *pcm, const long *utt_off, in
     if (ns + 16 > h->pcm_cap) { cudaFree(h->d_pcm); h->d_pcm = nullptr; LPS_CUDA(cudaMalloc(&h->d_pcm, (ns + 16) * sizeof(int16_t))); h->pcm_cap = ns + 16; }
     const size_t no = (size_t)total * LPS_BINS;
     if (no > h->out_cap) { cudaFree(h->d_out); h->d_out = nullptr; LPS_CUDA(cudaMalloc(&h->d_out, (no + 1) * sizeof(float))); h->out_cap = no + 1; }
-    LPS_CUDA(cudaMemcpyAsync(h->d_pcm, pcm + utt_off[0], ns * sizeof(int16_t), cudaMemcpyHostToDevice, h->s));
-    rc = run_kernel(h, h->d_pcm, n_utts, total, h->d_out, flags);
+    rc = check_flags(h, flags);
     if (rc) return rc;
-    if (no) LPS_CUDA(cudaMemcpyAsync(out, h->d_out, no * sizeof(float), cudaMemcpyDeviceToHost, h->s));
+    // Pipeline in pieces of PIECE frames on two streams: the upload of piece i+1 and the download of piece i-1 run
+    // under the kernel of piece i (PCIe is full duplex; the whole call is bound by the 1 028 B/frame going back).
+    const long long PIECE = 32768;
+    const int npieces = (int)((total + PIECE - 1) / PIECE);
+    while ((int)h->pe.size() < 2 * npieces + 2) { cudaEvent_t e; LPS_CUDA(cudaEventCreate(&e)); h->pe.push_back(e); }
+    LPS_CUDA(cudaStreamSynchronize(h->s));     // the offset table (uploaded on h->s) is visible to both streams
+    // sample position (relative to the uploaded span) of the first sample of global frame f
+    auto frame_sample = [&](long long f) {
+        int lo = 0, hi = n_utts;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tab[n_utts + 1 + mid] <= f) lo = mid; else hi = mid; }
+        return tab[lo] + (f - tab[n_utts + 1 + lo]) * LPS_FRAME_SHIFT;
+    };
+    for (int p = 0; p < npieces; p++) {
+        cudaStream_t st = (p & 1) ? h->s2 : h->s;
+        const long long f0 = (long long)p * PIECE, f1 = (f0 + PIECE < total) ? f0 + PIECE : total;
+        const long long s0 = frame_sample(f0), s1 = frame_sample(f1 - 1) + LPS_FRAME_LEN;
+        LPS_CUDA(cudaMemcpyAsync(h->d_pcm + s0, pcm + utt_off[0] + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        LPS_CUDA(cudaEventRecord(h->pe[2 * p], st));
+        rc = launch_frames(h, h->d_pcm, n_utts, f0, f1, h->d_out, flags, st);
+        if (rc) return rc;
+        LPS_CUDA(cudaEventRecord(h->pe[2 * p + 1], st));
+        LPS_CUDA(cudaMemcpyAsync(out + f0 * LPS_BINS, h->d_out + f0 * LPS_BINS, (size_t)(f1 - f0) * LPS_BINS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     LPS_CUDA(cudaStreamSynchronize(h->s));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, h->e0, h->e1);
-    h->last_ms = ms;
+    LPS_CUDA(cudaStreamSynchronize(h->s2));
+    double ms_sum = 0;
+    for (int p = 0; p < npieces; p++) { float ms = 0; cudaEventElapsedTime(&ms, h->pe[2 * p], h->pe[2 * p + 1]); ms_sum += ms; }
+    h->last_ms = ms_sum;
     if (total_frames) *total_frames = (long)total;
     return 0;
 }

@@ -15,18 +15,21 @@ static void usage(const char *a0)
     fprintf(stderr, "\r\nUSAGE:   %s infile HTK_outfile [options]\r\n\r\nOPTIONS:\r\n"
                     "     -q            Quiet Mode\r\n     -F    format  Input file format (RAW)\r\n"
                     "     -fs   freq    Sampling frequency in kHz (16)\r\n     -swap         Change input byte ordering\r\n"
-                    "     -gpu  n       CUDA device (default 0)\r\n", a0);
+                    "     -gpu  n       CUDA device (default 0)\r\n"
+                    "     -fast         register-resident FFT kernel (features within 1e-4 relative of the reference) instead of\r\n"
+                    "                   the reference's own butterfly network (default: byte-identical HTK files)\r\n", a0);
 }
 
 int main(int argc, char **argv)
 {
     const char *in = nullptr, *out = nullptr;
-    bool quiet = false, swap = false;
+    bool quiet = false, swap = false, fast = false;
     int gpu = 0, fs = 16;
     std::string fmt = "RAW";
     for (int i = 1; i < argc; i++) {          // ParseCommLine, Wav2LogSpec_be.c:127-259
         if (!strcmp(argv[i], "-q")) quiet = true;
         else if (!strcmp(argv[i], "-swap")) swap = true;
+        else if (!strcmp(argv[i], "-fast")) fast = true;
         else if (!strcmp(argv[i], "-F") && i + 1 < argc) fmt = argv[++i];
         else if (!strcmp(argv[i], "-fs") && i + 1 < argc) fs = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-gpu") && i + 1 < argc) gpu = atoi(argv[++i]);
@@ -51,7 +54,7 @@ int main(int argc, char **argv)
     std::vector<float> feat((size_t)nf * LPS_BINS);
     lps_handle *h = nullptr;
     if (lps_create(gpu, &h) != 0) { fprintf(stderr, "ERROR:   %s\r\n", lps_last_error()); return 1; }
-    if (lps_extract(h, pcm.data(), (long)pcm.size(), feat.data(), LPS_FLAG_BIG_ENDIAN) != 0) { fprintf(stderr, "ERROR:   %s\r\n", lps_last_error()); return 1; }
+    if (lps_extract(h, pcm.data(), (long)pcm.size(), feat.data(), LPS_FLAG_BIG_ENDIAN | (fast ? 0 : LPS_FLAG_EXACT)) != 0) { fprintf(stderr, "ERROR:   %s\r\n", lps_last_error()); return 1; }
     lps_destroy(h);
     FILE *fo = fopen(out, "wb");
     if (!fo) { fprintf(stderr, "ERROR:   Could not open file '%s' !\r\n", out); return 1; }

@@ -3,7 +3,7 @@ import ctypes as C
 import numpy as np
 from .bp_gpu import load_library
 
-FLAG_BIG_ENDIAN, FLAG_ZSCORE = 1, 2
+FLAG_BIG_ENDIAN, FLAG_ZSCORE, FLAG_EXACT = 1, 2, 4
 PF = C.POINTER(C.c_float)
 PS = C.POINTER(C.c_int16)
 PL = C.POINTER(C.c_long)
