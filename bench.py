@@ -137,21 +137,47 @@ def bench_lps(pkg, torch, dev, peaks, with_cpu):
     res["e2e"] = {"value": nf / dt, "unit": "frames/s", "h2d_bytes": int(h.nbytes), "d2h_bytes": int(feats.nbytes)}
     if with_cpu:
         try:
-            from oracle import oracle as O, refcuda
-            sample = h[:16000 * 60]
-            if refcuda.available("Wav2LPS_be_ref"):
-                with quiet_stdout():
-                    _, dtc = refcuda.ref_wav2lps(sample)
-                kind = "reference"
-            else:
-                t0 = time.perf_counter(); O.lps_extract(sample); dtc = time.perf_counter() - t0
-                kind = "port"
-            res["cpu_baseline"] = {"value": pkg.lps_nframes(len(sample)) / dtc, "unit": "frames/s", "cores": 1, "kind": kind,
-                                   "sample": "60 s of the same noise through %s (one process, incl. file I/O)" % ("oracle/_ref/Wav2LPS_be_ref (-O2)" if kind == "reference" else "oracle/lps_oracle.c")}
+            res["cpu_baseline"] = lps_cpu_baseline(pkg, h[:16000 * 60])
         except Exception as ex2:
             res["cpu_baseline"] = {"unavailable": str(ex2)[:200]}
     ex.close()
     return res
+
+
+def lps_cpu_baseline(pkg, sample):
+    """the reference's Wav2LPS_be (built unmodified into oracle/_ref, its own -O0 flags and -O2), one
+    process per host core on 60 s of the same noise each, aggregate frames/s; falls back to the C oracle port."""
+    import tempfile
+    from oracle import oracle as O, refcuda
+    cores = host_cores()
+    nf = pkg.lps_nframes(len(sample))
+    out = {"unit": "frames/s", "cores": cores}
+    bins = [("O2", "Wav2LPS_be_ref"), ("O0", "Wav2LPS_be_ref_O0")]
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    have = [(tag, os.path.join(ref_dir, b)) for tag, b in bins if os.path.exists(os.path.join(ref_dir, b))]
+    if not have:
+        t0 = time.perf_counter(); O.lps_extract(sample); dtc = time.perf_counter() - t0
+        out.update({"value": nf / dtc, "cores": 1, "kind": "port", "sample": "60 s of noise through oracle/lps_oracle.c, one thread"})
+        return out
+    with tempfile.TemporaryDirectory() as td:
+        raw = os.path.join(td, "in.raw")
+        sample.astype("<i2").tofile(raw)
+        for tag, exe in have:
+            def run(n):
+                ps = [subprocess.Popen([exe, "-F", "RAW", "-fs", "16", raw, os.path.join(td, "o%d.lps" % i)],
+                                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i in range(n)]
+                t0 = time.perf_counter()
+                for q in ps:
+                    q.wait()
+                return time.perf_counter() - t0
+            t1 = run(1)
+            tn = run(cores)
+            out["per_core_%s" % tag] = nf / t1
+            out["all_cores_%s" % tag] = cores * nf / tn
+    out["value"] = out.get("all_cores_O2", out.get("all_cores_O0"))
+    out["kind"] = "reference"
+    out["sample"] = "60 s of the same noise per process through oracle/_ref/Wav2LPS_be_ref (reference sources, -O2; -O0 = its own makefile flags), %d processes at once, incl. file I/O" % cores
+    return out
 
 
 class quiet_stdout:
@@ -168,6 +194,28 @@ class quiet_stdout:
         os.close(self.null); os.close(self.saved)
 
 
+def omp_threads(want=None):
+    """Sets (before the oracle library is first loaded) and reports the OpenMP thread count the C oracle really runs with.
+    torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: without this the CPU arm would silently run on one core."""
+    import ctypes
+    if want:
+        os.environ["OMP_NUM_THREADS"] = str(want)
+    try:
+        g = ctypes.CDLL("libgomp.so.1")
+        if want:
+            g.omp_set_num_threads(int(want))
+        return int(g.omp_get_max_threads())
+    except OSError:
+        return 1
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def make_net_inputs(ls, seed=1):
     from oracle import oracle as O
     return O.init_weights(ls, seed=seed, beta=2.0)
@@ -179,6 +227,7 @@ def run_reference(args, ls, ml, beta, bunch):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = omp_threads(host_cores())
     from oracle import oracle as O
     O.build()
     W, b = make_net_inputs(ls)
@@ -196,15 +245,123 @@ def run_reference(args, ls, ml, beta, bunch):
         done += 1
     dt = time.time() - t0
     val = done * bunch / dt
-    cores = os.cpu_count()
+    cores = threads
     line = {"impl": "reference", "metric": "train_frames_per_sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "timed_steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "bunch": bunch, "layersizes": ls, "MLflag": ml, "shapefactor": beta},
+            "config": {"workload": args.workload, "bunch": bunch, "layersizes": ls, "MLflag": ml, "shapefactor": beta,
+                       "note": "the reference has no CPU trainer and no multi-GPU path: this arm is its training step restated in C "
+                               "(oracle/ggd_oracle.c) on the host cores, one bunch of %d frames per step at every N" % bunch},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d bunches of %d frames through oracle/ggd_oracle.c (OpenMP, %d threads)" % (done, bunch, cores)},
+                             "sample": "%d bunches of %d frames through oracle/ggd_oracle.c (OpenMP, omp_get_max_threads() = %d)" % (done, bunch, cores)},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def dp_parity_leg(pkg, torch, dist, world, rank, local_rank, uid_fn):
+    """OUTSIDE the timed region: `world` ranks train a few sharded steps and rank 0 compares weights, alpha and the loss
+    trace with the C oracle on the UNSHARDED minibatch (tolerance 1e-3 relative), plus bit-identity of the
+    weights across ranks.  Two cases: a small ragged net (3 steps) and the named net (2 steps), 128 frames per GPU."""
+    from oracle import oracle as O
+    res = {"ok": True, "max_rel": 0.0, "bit_identical": True, "cases": []}
+    for name, ls, nb in (("small_70x96x80x33", [70, 96, 80, 33], 3), ("named_1799x2048x3_257", [1799, 2048, 2048, 2048, 257], 2)):
+        M = 128
+        rng = np.random.RandomState(13)
+        W, b = O.init_weights(ls, seed=3)
+        x = rng.randn(world, nb * M, ls[0]).astype(np.float32)
+        t = rng.randn(world, nb * M, ls[-1]).astype(np.float32)
+        net = pkg.BP_GPU(0, local_rank, len(ls), ls, M, LR, MOM, WC, W, b, 1.5, 1, world_size=world, rank=rank, nccl_unique_id=uid_fn())
+        net.train(nb * M, x[rank], t[rank])
+        Wn, bn = net.returnWeights()
+        alpha, losses = net.alpha(), net.losses()
+        net.close()
+        flat = np.concatenate([w.ravel() for w in Wn + bn]).astype(np.float32)
+        mine = torch.from_numpy(flat.view(np.int32).copy()).cuda()
+        lo_, hi_ = mine.clone(), mine.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo_, hi_))
+        case = {"net": name, "steps": nb, "global_minibatch": M * world, "bit_identical_across_ranks": same}
+        if rank == 0:
+            xg = np.concatenate([x[:, i * M:(i + 1) * M].reshape(world * M, -1) for i in range(nb)])
+            tg = np.concatenate([t[:, i * M:(i + 1) * M].reshape(world * M, -1) for i in range(nb)])
+            orc = O.OracleNet(ls, world * M, LR, MOM, WC, 1.5, 1, W, b)
+            lo, al = orc.train(xg, tg)
+            Wo, bo = orc.weights()
+            rel = lambda a, c: float(np.linalg.norm(np.asarray(a, np.float64) - c) / max(np.linalg.norm(np.asarray(c, np.float64)), 1e-30))
+            case["rel_weights"] = max(rel(a, c) for a, c in zip(Wn + bn, Wo + bo))
+            case["rel_update"] = max(rel(a - w0, c - w0) for a, c, w0 in zip(Wn, Wo, W))
+            case["rel_alpha"] = rel(alpha, al[-1])
+            case["rel_loss"] = float(np.max(np.abs(losses - lo) / np.abs(lo)))
+            worst = max(case["rel_weights"], case["rel_alpha"], 0.5 * case["rel_update"])
+            res["max_rel"] = max(res["max_rel"], worst)
+            res["ok"] = res["ok"] and worst <= 1e-3 and case["rel_loss"] <= 5e-3
+        res["bit_identical"] = res["bit_identical"] and same
+        res["ok"] = res["ok"] and same
+        res["cases"].append(case)
+    return res
+
+
+def config4_record(pkg, torch, dist, world, rank, local_rank, uid_fn, peaks, steps=100):
+    """BASELINE.json configs[3]: 2827-2048^3-257 (ctx 11), GLOBAL minibatch 1024 sharded as 1024/world frames per GPU
+    (strong scaling: the update runs replicated over all 1024 frames on every rank).  Device-resident, CUDA events."""
+    ls, ml, beta, _ = WORKLOADS["ggd_ml_2827x2048x3_257_g1024"]
+    bunch = 1024 // world
+    dev = torch.device("cuda", local_rank)
+    W, b = make_net_inputs(ls)
+    net = pkg.BP_GPU(0, local_rank, len(ls), ls, bunch, LR, MOM, WC, W, b, beta, ml, world_size=world, rank=rank,
+                     nccl_unique_id=uid_fn() if world > 1 else None)
+    g = torch.Generator(device=dev); g.manual_seed(11 + rank)
+    n = steps * bunch
+    d_in = torch.randn(n, ls[0], device=dev, generator=g); d_tg = torch.randn(n, ls[-1], device=dev, generator=g)
+    net.reserve(n)
+    net.train_device(min(n, 16 * bunch), d_in.data_ptr(), d_tg.data_ptr())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    net.train_device(n, d_in.data_ptr(), d_tg.data_ptr())
+    ms = net.stats()["device_ms"]
+    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    kt = net.profile_kernels(min(16, steps) * bunch, d_in.data_ptr(), d_tg.data_ptr())
+    net.close()
+    P = sum(ls[i] * ls[i + 1] for i in range(len(ls) - 1)) + sum(ls[1:])
+    upd_ms = kt["dw_update"]["ms"] / max(kt["steps"], 1)
+    fpf = flops_per_frame(ls)
+    return {"workload": "ggd_ml_2827x2048x3_257_g1024", "frames_per_gpu_per_step": bunch, "global_minibatch": 1024, "steps": steps,
+            "scaling": "strong", "value": steps * 1024 / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps,
+            "tensor_frac_whole_step": fpf * 1024 * steps / (ms * 1e-3) / 1e12 / peaks["bf16_sus"] / world,
+            "roofline": {"bound": "hbm", "kernel": "dw_wide_kernel (dW over all 1024 frames + momentum update, replicated per rank)",
+                         "achieved": 16.0 * P / (upd_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": 16.0 * P / (upd_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                         "tflops_executed_bf16x3": 3 * 2.0 * P * 1024 / (upd_ms * 1e-3) / 1e12,
+                         "note": "16 B/param algorithmic; at 1024 frames the kernel is bound by the tensor pipe / operand fabric, not HBM"}}
+
+
+def chain_trace(pkg, net, ls, bunch, torch, dev):
+    """Device-side timeline of ONE training step in stream order with PDL (per launch: first CTA entry -> last CTA exit,
+    globaltimer): kernel durations without the launch / event overhead of the per-launch event pairs."""
+    import ctypes as C
+    L = pkg.load_library()
+    PF = C.POINTER(C.c_float)
+    L.ggd_debug_trace_step.argtypes = [C.c_void_p, PF, PF, C.c_int, PF, C.c_int, C.POINTER(C.c_int)]
+    rng = np.random.RandomState(0)
+    x = rng.randn(bunch, ls[0]).astype(np.float32); t = rng.randn(bunch, ls[-1]).astype(np.float32)
+    out = np.zeros((32, 12), np.float32); n = C.c_int()
+    rc = L.ggd_debug_trace_step(net.h, x.ctypes.data_as(PF), t.ctypes.data_as(PF), 1, out.ctypes.data_as(PF), 32, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(L.ggd_last_error().decode())
+    rows = out[:n.value]
+    kinds = {0: "fwd_gemm", 2: "dx_gemm", 3: "dw_gemm"}
+    per = {}
+    for r in rows:
+        k = kinds.get(int(r[0]), "other")
+        per.setdefault(k, []).append(float(r[3] - r[2]))
+    return {"launch_us": {k: [round(v, 2) for v in vs] for k, vs in per.items()},
+            "class_us": {k: float(sum(vs)) for k, vs in per.items()},
+            "chain_us": float(rows[:, 3].max() - rows[:, 2].min()) if len(rows) else None,
+            "how": "ggd_debug_trace_step: globaltimer stamps of every CTA, stream order with programmatic dependent launch"}
 
 
 def main():
@@ -218,6 +375,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lps", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the data-parallel parity leg (N > 1)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 sub-record")
     args = ap.parse_args()
     ls, ml, beta, bunch = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -236,11 +395,16 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     uid = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+
+    def new_uid():
         box = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        uid = box[0]
+        return box[0]
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        uid = new_uid()
+    threads = omp_threads(host_cores())      # the C oracle (parity leg, CPU baseline) uses the host cores, not torchrun's OMP_NUM_THREADS=1
 
     def barrier():
         if world > 1:
@@ -251,7 +415,8 @@ def main():
     prec = 0 if args.precision == "bf16x3" else 1
     net = pkg.BP_GPU(0, local_rank, len(ls), ls, bunch, LR, MOM, WC, W, b, beta, ml, precision=prec, world_size=world, rank=rank,
                      nccl_unique_id=uid)
-    K, Wm = args.steps, max(args.warmup, 3)
+    # warm-up: at least 32 steps so that BOTH step graphs (16-step and single-step) have been uploaded and replayed once
+    K, Wm = args.steps, max(args.warmup, 35)      # 2 x 16-step graph + 3 single-step graphs
     nfr = K * bunch
     g = torch.Generator(device=dev); g.manual_seed(1 + rank)
     d_in = torch.randn(max(nfr, Wm * bunch), ls[0], device=dev, generator=g)        # synthetic frames, resident in HBM
@@ -260,7 +425,7 @@ def main():
     net.reserve(max(nfr, Wm * bunch))
     net.train_device(Wm * bunch, d_in.data_ptr(), d_tg.data_ptr())
     barrier()
-    # ---- timed region: K steps, inputs already resident; the input set (737 MB + weights) exceeds the 126 MB L2
+    # ---- timed region: K steps, inputs already resident (800 steps: 842 MB of frames + 101 MB of weight state vs the 126 MB L2)
     sampler = ClockSampler(local_rank); sampler.start()
     time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,6 +445,7 @@ def main():
     clocks = sampler.finish()
     value = K * bunch * world / (ms * 1e-3)
 
+    resident_bytes = int(d_in.numel() * 4 + d_tg.numel() * 4)
     # ---- e2e: the public call with HOST (pinned) buffers: H2D of the chunk + steps + D2H of the loss trace
     e2e = None
     if not args.no_e2e:
@@ -311,72 +477,98 @@ def main():
     per_step = {k: (kt[k]["ms"] / steps_p, kt[k]["launches"] // max(steps_p, 1)) for k in kt if isinstance(kt[k], dict)}
     fpf = flops_per_frame(ls)
     P = sum(ls[i] * ls[i + 1] for i in range(len(ls) - 1)); P1 = ls[0] * ls[1]
+    Preal = P + sum(ls[1:])
     gemm_flops = {"fwd_gemm": 2 * P * bunch, "dw_gemm": 2 * P * bunch, "dx_gemm": 2 * (P - P1) * bunch}
     kern = {}
+    # In-stream device timeline of one step (N = 1): per-launch durations without launch / event overhead.  The per-launch event
+    # pairs of ggd_profile_kernels break the programmatic-dependent-launch overlap and add ~7 us per launch, so they overstate
+    # the GEMM classes; where the trace exists it supplies the roofline numerators and the event-pair times stay as `ms_event_pair`.
+    trace = None
+    if world == 1 and prec == 0:
+        try:
+            trace = chain_trace(pkg, net, ls, bunch, torch, dev)
+        except Exception as ex:
+            trace = {"unavailable": str(ex)[:200]}
+    tr_us = (trace or {}).get("class_us", {})
     for k, (msk, n) in per_step.items():
         if n == 0:
             continue
-        ent = {"ms_per_step": msk, "launches_per_step": n}
+        ent = {"ms_per_step": msk, "launches_per_step": n, "timing": "CUDA-event pair around every launch (no graph)"}
+        if k in tr_us and tr_us[k] > 0:
+            ent["ms_event_pair"] = msk
+            ent["ms_per_step"] = msk = tr_us[k] * 1e-3
+            ent["timing"] = "device globaltimer, first CTA entry -> last CTA exit per launch, stream order with PDL"
+        if k == "dw_update" and trace and trace.get("chain_us"):
+            ent["ms_event_pair"] = msk
+            ent["ms_per_step"] = msk = max(ms / K - trace["chain_us"] * 1e-3, 1e-6)
+            ent["timing"] = "graph step time minus the traced forward/backward chain"
         if k in gemm_flops:
             ent["tflops"] = gemm_flops[k] / (msk * 1e-3) / 1e12
             ent["frac_of_bf16_sustained"] = ent["tflops"] / peaks["bf16_sus"]
         if k == "dw_update":
-            Ppad = kt["param_elems"]      # padded weights + biases; the fused kernel streams W and delta once each way
-            ent["gbs"] = 16.0 * Ppad / (msk * 1e-3) / 1e9
-            ent["tflops"] = gemm_flops["dw_gemm"] / (msk * 1e-3) / 1e12
+            ent["gbs"] = 16.0 * Preal / (msk * 1e-3) / 1e9      # real (unpadded) weights + biases; W and delta once each way
+            ent["tflops"] = 2.0 * P * bunch * world / (msk * 1e-3) / 1e12     # the update runs over the WHOLE minibatch on every rank
         if k == "update":
-            if world > 1:
-                # push-model owner update (reduce_update_kernel): each rank updates 1/world of the parameters: read W, delta and `world`
-                # partial gradient tiles, write W, delta and the local copy of the shadows; the NVLink bytes are not HBM bytes of this rank
-                ent["gbs"] = (16.0 + 4.0 * world + 4.0) * kt["param_elems"] / world / (msk * 1e-3) / 1e9
-                ent["nvlink_gbs_out"] = 4.0 * kt["param_elems"] * (world - 1) / world / (msk * 1e-3) / 1e9
-            else:
-                ent["gbs"] = 20.0 * kt["param_elems"] / (msk * 1e-3) / 1e9     # read W, delta, g; write W, delta (+4 B shadows not counted)
-        if k == "dw_gemm" and world > 1:
-            ent["nvlink_gbs_out"] = 4.0 * kt["param_elems"] * (world - 1) / world / (msk * 1e-3) / 1e9   # gradient tiles pushed to their owners
+            ent["gbs"] = 20.0 * Preal / (msk * 1e-3) / 1e9          # read W, delta, g; write W, delta (+4 B shadows not counted)
+        if k == "factor_push":
+            fbytes = 4.0 * bunch * (sum((u + 63) // 64 * 64 for u in ls[:-1]) + sum((u + 63) // 64 * 64 for u in ls[1:]))
+            ent["nvlink_bytes_out_per_step"] = fbytes * (world - 1)
         if k == "loss":
             ent["gbs"] = (3 * 4 * bunch * 257 + 1028) / (msk * 1e-3) / 1e9
         kern[k] = ent
-    # ---- rooflines.  Every kernel class gets one (GEMMs: tensor pipe with SURVEY 8d's FLOPs; update: HBM with 16 B/param); the
-    # headline `roofline` is the kernel SYMBOL with the largest share of the step (the forward class is two symbols: L-2 sigmoid
-    # launches + 1 output-layer launch), which is what the committed ncu launch list shows as its top line.
-    def symbol_share(k):
-        e = kern[k]
-        return e["ms_per_step"] * ((e["launches_per_step"] - 1) / e["launches_per_step"] if k == "fwd_gemm" and e["launches_per_step"] > 1 else 1.0)
+    # ---- rooflines.  Every kernel class gets one (GEMMs: tensor pipe with SURVEY 8d's FLOPs; update: HBM with 16 B/param).
+    # The headline `roofline` is the kernel with the largest share of the step: the forward and dE/dx launches are one kernel
+    # template (gemm_tc_kernel), so they are taken together.
     roofs = {}
+    prof = lambda name: os.path.join(ROOT, "profiles", name)
+    named = ls == [1799, 2048, 2048, 2048, 257] and bunch == 128
     for k, e in kern.items():
         if k in gemm_flops:
             roofs[k] = {"bound": "tensor", "kernel": "gemm_tc_kernel (%s, %d launches/step)" % (k, e["launches_per_step"]), "achieved": e["tflops"],
                         "peak": peaks["bf16_sus"], "unit": "TFLOP/s", "frac": e["tflops"] / peaks["bf16_sus"], "traffic": None,
-                        "peak_source": peaks["src"] + " bf16 sustained; algorithmic FLOPs (the pipe executes 3x: bf16x3)",
-                        "traffic_source": None,
-                        "note": "128-frame GEMMs are bound by the weight stream, not the tensor pipe: 2*128 FLOP per 4-byte weight = 64 FLOP/B against "
-                                "a machine balance of ~210 FLOP/B; see gemm_tensor_probe for the same kernel at tensor-bound sizes"}
-            gp = os.path.join(ROOT, "profiles", "r01h_gemm_traffic.json")
-            if k == "fwd_gemm" and os.path.exists(gp) and ls == [1799, 2048, 2048, 2048, 257]:
-                gj = json.load(open(gp))
-                roofs[k]["traffic"] = gj["traffic_bytes_per_launch"]          # DRAM bytes of one 128x2048x2048 launch (ncu --set full)
-                roofs[k]["traffic_source"] = gj["source"]
-                roofs[k]["l2_to_sm_bytes_per_launch"] = gj["l2_to_sm_bytes"]
+                        "peak_source": peaks["src"] + " bf16 sustained; algorithmic FLOPs (the pipe executes 3x: bf16x3)", "timing": e["timing"]}
+            for cand in ("r02_%s_traffic.json" % k, "r01h_gemm_traffic.json" if k == "fwd_gemm" else ""):
+                if cand and named and os.path.exists(prof(cand)):
+                    gj = json.load(open(prof(cand)))
+                    roofs[k]["traffic"] = gj["traffic_bytes_per_launch"]          # DRAM bytes of one launch (ncu --set full)
+                    roofs[k]["traffic_source"] = gj["source"]
+                    if "l2_to_sm_bytes" in gj:
+                        roofs[k]["l2_to_sm_bytes_per_launch"] = gj["l2_to_sm_bytes"]
+                    break
         elif "gbs" in e and k in ("dw_update", "update"):
             roofs[k] = {"bound": "hbm", "kernel": k, "achieved": e["gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": e["gbs"] / peaks["hbm"],
-                        "traffic": None, "peak_source": peaks["src"]}
+                        "traffic": None, "peak_source": peaks["src"], "timing": e["timing"]}
             if k == "dw_update":
-                roofs[k]["kernel"] = "dw_persist_kernel (dW GEMM + momentum update of all layers; 16 B/param algorithmic)"
-                tp = os.path.join(ROOT, "profiles", "r01h_dw_persist_traffic.json")
-                if os.path.exists(tp) and ls == [1799, 2048, 2048, 2048, 257]:
-                    tj = json.load(open(tp))
-                    roofs[k]["traffic"] = tj["traffic_bytes_per_launch"]
-                    roofs[k]["traffic_source"] = tj["source"]
-                roofs[k]["algorithmic_bytes_per_launch"] = 16 * kt["param_elems"]
-    dom = max(roofs, key=symbol_share) if roofs else None
-    roof = dict(roofs[dom]) if dom else None
-    if roof is not None:
-        roof["share_of_kernel_time"] = symbol_share(dom) / max(sum(e["ms_per_step"] for e in kern.values()), 1e-12)
+                roofs[k]["kernel"] = ("dw_persist_kernel" if (world == 1 and bunch <= 128) else "dw_wide_kernel") + \
+                    " (dW GEMM + momentum update of all layers; 16 B/param algorithmic)"
+                for cand in ("r02_dw_update_traffic.json", "r01h_dw_persist_traffic.json"):
+                    if named and world == 1 and os.path.exists(prof(cand)):
+                        tj = json.load(open(prof(cand)))
+                        roofs[k]["traffic"] = tj["traffic_bytes_per_launch"]
+                        roofs[k]["traffic_source"] = tj["source"]
+                        break
+                roofs[k]["algorithmic_bytes_per_launch"] = 16 * Preal
+    roof = None
+    if "fwd_gemm" in kern and "dx_gemm" in kern:
+        t_chain = kern["fwd_gemm"]["ms_per_step"] + kern["dx_gemm"]["ms_per_step"]
+        t_other = max((e["ms_per_step"] for k, e in kern.items() if k not in ("fwd_gemm", "dx_gemm")), default=0.0)
+        total = sum(e["ms_per_step"] for e in kern.values())
+        if t_chain >= t_other:
+            tf = (gemm_flops["fwd_gemm"] + gemm_flops["dx_gemm"]) / (t_chain * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (forward + dE/dx chain, %d launches/step)" % (kern["fwd_gemm"]["launches_per_step"] + kern["dx_gemm"]["launches_per_step"]),
+                    "achieved": tf, "peak": peaks["bf16_sus"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_sus"],
+                    "traffic": roofs["fwd_gemm"].get("traffic"), "traffic_note": "DRAM bytes of ONE 128x2048x2048 forward launch (ncu --set full)",
+                    "peak_source": roofs["fwd_gemm"]["peak_source"], "timing": kern["fwd_gemm"]["timing"],
+                    "executed_frac_bf16x3": 3 * tf / peaks["bf16_sus"], "share_of_kernel_time": t_chain / max(total, 1e-12),
+                    "note": "at %d frames per launch the chain is latency / weight-stream bound: 2*%d FLOP per 4-byte weight against a machine "
+                            "balance of ~210 FLOP/B; gemm_tensor_probe has the same kernel at tensor-bound sizes" % (bunch, bunch)}
+        else:
+            dom = max((k for k in roofs if k not in ("fwd_gemm", "dx_gemm")), key=lambda k: kern[k]["ms_per_step"])
+            roof = dict(roofs[dom]); roof["share_of_kernel_time"] = kern[dom]["ms_per_step"] / max(total, 1e-12)
 
     # ---- CPU baseline on rank 0 at N=1: the C oracle on a bounded sample of the same workload
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as O
         orc = O.OracleNet(ls, bunch, LR, MOM, WC, beta, ml, W, b)
         xs = d_in[:bunch].cpu().numpy(); ts = d_tg[:bunch].cpu().numpy()
@@ -385,8 +577,8 @@ def main():
         while n < 8 and time.time() - t0 < 20.0:
             orc.train_bunch(xs, ts); n += 1
         dtc = time.time() - t0
-        cpu = {"value": n * bunch / dtc, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d bunches of %d frames through oracle/ggd_oracle.c (OpenMP)" % (n, bunch)}
+        cpu = {"value": n * bunch / dtc, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d bunches of %d frames through oracle/ggd_oracle.c (OpenMP, omp_get_max_threads() = %d)" % (n, bunch, threads)}
 
     # ---- the reference's own CUDA trainer (BP_GPU.cu + DevFunc.cu + cuBLAS, built unmodified into oracle/_ref) on the
     #      same GPU, same shapes: reported next to ours, not the optimisation target
@@ -422,6 +614,20 @@ def main():
         except Exception as ex:
             probe = {"unavailable": str(ex)[:200]}
 
+    # ---- data-parallel parity leg and the config-4 record (outside the timed region; every rank takes part)
+    dp_parity = None
+    if world > 1 and not args.no_parity:
+        try:
+            dp_parity = dp_parity_leg(pkg, torch, dist, world, rank, local_rank, new_uid)
+        except Exception as ex:
+            dp_parity = {"ok": False, "error": str(ex)[:300]}
+    cfg4 = None
+    if not args.no_config4 and args.workload != "ggd_ml_2827x2048x3_257_g1024":
+        try:
+            cfg4 = config4_record(pkg, torch, dist, world, rank, local_rank, new_uid, peaks)
+        except Exception as ex:
+            cfg4 = {"error": str(ex)[:300]}
+
     # ---- LPS front end (second half of the metric): frames/s of the extraction kernel on synthetic 16 kHz noise
     lps = None
     if rank == 0 and not args.no_lps:
@@ -433,10 +639,13 @@ def main():
                 "dtype": "bf16x3 (bf16 hi+lo operands, fp32 TMEM accumulate, fp32 master weights)" if prec == 0 else "f32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "layersizes": ls, "MLflag": ml, "shapefactor": beta, "frames_per_gpu_per_step": bunch,
-                           "global_minibatch": bunch * world, "l2": "inputs (737 MB/chunk) and weight state (250 MB) exceed the 126 MB L2",
-                           "parallelism": "dp%d (frame-sharded; allreduce of sum|e|^beta and of the gradients)" % world},
+                           "global_minibatch": bunch * world,
+                           "l2": "every step reads %d new input bytes and streams the %.0f MB of weights + momentum; resident chunk %.0f MB vs the 126 MB L2%s"
+                                 % (bunch * (ls[0] + ls[-1]) * 4, 8.0 * Preal / 1e6, resident_bytes / 1e6,
+                                    "" if resident_bytes + 8 * Preal > 126e6 else " (short run: raise --steps for a chunk larger than L2)"),
+                           "parallelism": "dp%d (frames sharded; sum|e|^beta and the gradient FACTORS exchanged over NVLink peer memory, update replicated)" % world},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_all": roofs, "cpu_baseline": cpu,
-                "kernels": kern, "gemm_tensor_probe": probe, "flops_per_frame": fpf, "reference_cuda": ref_cuda, "lps": lps,
+                "kernels": kern, "step_trace": trace, "dp_parity": dp_parity, "config4": cfg4, "gemm_tensor_probe": probe, "flops_per_frame": fpf, "reference_cuda": ref_cuda, "lps": lps,
                 "tensor_frac_whole_step": (fpf * bunch * K / (ms * 1e-3) / 1e12) / peaks["bf16_sus"]}
         print(json.dumps(line), flush=True)
     net.close()

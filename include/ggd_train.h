@@ -118,6 +118,14 @@ int ggd_train_device(ggd_handle *h, int n_frames, const float *d_in, const float
 int ggd_cv_sqerr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result);
 int ggd_cv_abserr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result);
 int ggd_cv_loglik(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result);
+/* The three CV metrics of BPtrain.cc:124-128 from ONE forward pass: result3 = {CrossValid, CrossValiddB, CrossValid2}
+ * (CrossValid2 is 0 unless MLflag == 1); identical values to the three separate calls. */
+int ggd_cv_all(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result3);
+/* Inference path of Test_code/decode.m:28-62 + frame_expand.m:6-25 for ONE utterance: z-score of the raw LPS frames
+ * lps[n_frames][fea_dim] with the .norm constants, fea_context (odd) frames of context with the first / last frame
+ * replicated at the utterance edges, forward pass, de-normalisation out/dvar + mean.  out: n_frames x layersizes[last]. */
+int ggd_enhance(ggd_handle *h, int n_frames, const float *lps, int fea_dim, int fea_context, const float *mean, const float *dvar,
+                float *out);
 /* forward only: out is n_frames x layersizes[last] (cv_bunch_single, BP_GPU.cu:442-512) */
 int ggd_forward(ggd_handle *h, int n_frames, const float *in, float *out);
 

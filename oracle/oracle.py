@@ -189,6 +189,29 @@ class OracleNet:
 
 # ---------------------------------------------------------------------------------------------
 # LPS
+def frame_expand(feature, context_num):
+    """Test_code/frame_expand.m:6-25: per frame t the frames t-c..t+c, the first / last frame replicated at the edges"""
+    T = feature.shape[0]
+    half = (context_num - 1) // 2
+    idx = np.clip(np.arange(T)[:, None] + np.arange(-half, half + 1)[None, :], 0, T - 1)
+    return feature[idx].reshape(T, -1)
+
+
+def enhance_ref(lps, W, b, layersizes, mean, dvar, context_num):
+    """Test_code/decode.m:28-62 restated in float64 (MATLAB arithmetic): z-score, frame_expand, sigmoid layers, linear
+    output, de-normalisation.  W[l] in the .wts order (index = out + in*cur).  (decode.m round-trips the expanded input
+    through an 8-digit ASCII file, input_lsp.txt; that quantisation, ~1e-8 relative, is not reproduced.)"""
+    x = (np.asarray(lps, np.float64) - mean) * dvar
+    y = frame_expand(x, context_num)
+    L = len(layersizes)
+    for l in range(1, L):
+        Wm = np.asarray(W[l - 1], np.float64).reshape(layersizes[l - 1], layersizes[l])     # [in][out]
+        y = y @ Wm + np.asarray(b[l - 1], np.float64)
+        if l < L - 1:
+            y = 1.0 / (1.0 + np.exp(-y))
+    return y / dvar + mean
+
+
 def lps_extract(pcm):
     pcm = np.ascontiguousarray(pcm, np.int16)
     L = lib()

@@ -61,6 +61,8 @@ def load_library():
         for f in ("ggd_cv_sqerr", "ggd_cv_abserr", "ggd_cv_loglik"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int, PF, PF, PF]
         L.ggd_forward.argtypes = [C.c_void_p, C.c_int, PF, PF]
+        L.ggd_cv_all.argtypes = [C.c_void_p, C.c_int, PF, PF, PF]
+        L.ggd_enhance.argtypes = [C.c_void_p, C.c_int, PF, C.c_int, C.c_int, PF, PF, PF]
         L.ggd_get_weights.argtypes = [C.c_void_p, C.POINTER(PF), C.POINTER(PF)]
         L.ggd_get_alpha.argtypes = [C.c_void_p, PF]
         L.ggd_get_losses.argtypes = [C.c_void_p, PF, C.c_int, C.POINTER(C.c_int)]
@@ -196,6 +198,20 @@ class BP_GPU:
 
     def CrossValid2(self, n_frames, in_, targ):
         return self._cv(self.L.ggd_cv_loglik, n_frames, in_, targ)
+
+    def CrossValidAll(self, n_frames, in_, targ):
+        """(CrossValid, CrossValiddB, CrossValid2) from one forward pass"""
+        in_, targ = _f32(in_), _f32(targ)
+        r = (C.c_float * 3)()
+        self._ck(self.L.ggd_cv_all(self.h, n_frames, _fp(in_), _fp(targ), C.cast(r, PF)))
+        return r[0], r[1], r[2]
+
+    def enhance(self, lps, mean, dvar, fea_context):
+        """Test_code/decode.m for one utterance: raw LPS frames [T][fea_dim] -> enhanced LPS [T][layersizes[-1]]"""
+        lps, mean, dvar = _f32(lps), _f32(mean), _f32(dvar)
+        out = np.zeros((lps.shape[0], self.layersizes[-1]), np.float32)
+        self._ck(self.L.ggd_enhance(self.h, lps.shape[0], _fp(lps), lps.shape[1], fea_context, _fp(mean), _fp(dvar), _fp(out)))
+        return out
 
     def returnWeights(self):
         n = self.numlayers

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) factor_push_kernel(const FxPushArgs a)
             __threadfence_system();
             if (a.trace) a.trace[a.event * 4 + 2] = gtime();
             for (int p = 0; p < a.world; p++)
-                if (p != a.rank) st_release_sys_u32(a.peer_flags[p] + a.rank * FX_STRIDE + a.event, step);
+                if (p != a.rank) st_relaxed_sys_u32(a.peer_flags[p] + a.rank * FX_STRIDE + a.event, step);
             if (a.trace) a.trace[a.event * 4 + 3] = gtime();
         }
     }
@@ -82,69 +82,6 @@ __global__ void __launch_bounds__(256) factor_push_kernel(const FxPushArgs a)
 void launch_factor_push(const FxPushArgs &a, int grid, cudaStream_t s)
 {
     factor_push_kernel<<<grid, 256, 0, s>>>(a);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int BW_COLS = 32, BW_ROWL = 32;
-__global__ void __launch_bounds__(BW_COLS *BW_ROWL) bias_wide_kernel(const BiasWideArgs a)
-{
-    __shared__ float red[BW_ROWL][BW_COLS + 1];
-    const BiasWideLayer L = a.layer[blockIdx.y];
-    const int tx = threadIdx.x % BW_COLS, ty = threadIdx.x / BW_COLS;
-    const int n = blockIdx.x * BW_COLS + tx;
-    const bool active = blockIdx.x * BW_COLS < L.N;
-    if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.trace[FX_TRACE_BIAS] = gtime();
-    if (active && a.world > 1 && L.ev_dx >= 0) {
-        const unsigned int step = *a.bias_step + 1u;
-        if (threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
-            const unsigned int *f = a.flags + threadIdx.x * FX_STRIDE + L.ev_dx;
-            const long long t0 = clock64();
-            while ((int)(ld_acquire_sys_u32(f) - step) < 0) {
-                if (clock64() - t0 > (1ll << 33)) {
-                    *a.error_flag = 1u + threadIdx.x;
-                    __threadfence_system();
-                    hang_report(a.hang, 300 + L.ev_dx, (int)step, threadIdx.x);
-                }
-                __nanosleep(64);
-            }
-        }
-        __syncthreads();
-    }
-    if (active) {
-        float s = 0.0f;
-        if (n < L.N)
-            for (int m = ty; m < a.rows; m += BW_ROWL) s += join_bf16(L.hi[(size_t)m * L.ld + n], L.lo[(size_t)m * L.ld + n]);
-        red[ty][tx] = s;
-        __syncthreads();
-        if (ty == 0 && n < L.N) {
-            float g = red[0][tx];
-#pragma unroll
-            for (int r = 1; r < BW_ROWL; r++) g += red[r][tx];     // fixed order: identical on every rank
-            const float db = a.mom * L.db[n] - a.lr * (g / a.Mg);   // no weight cost on biases (BP_GPU.cu:435)
-            L.db[n] = db;
-            L.b[n] = db + L.b[n];
-        }
-    }
-    // last block out counts the bias step (every block has read the counter above)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int total = gridDim.x * gridDim.y;
-        const unsigned int prev = atomicAdd(a.block_counter, 1u);
-        if (prev == total - 1) {
-            *a.block_counter = 0;
-            *a.bias_step += 1u;
-            if (a.trace) a.trace[FX_TRACE_BIAS + 1] = gtime();
-        }
-    }
-}
-
-void launch_bias_wide(const BiasWideArgs &a, cudaStream_t s)
-{
-    int maxn = 1;
-    for (int l = 0; l < a.nlayers; l++) maxn = a.layer[l].N > maxn ? a.layer[l].N : maxn;
-    dim3 grid(ceil_div(maxn, BW_COLS), a.nlayers);
-    bias_wide_kernel<<<grid, BW_COLS * BW_ROWL, 0, s>>>(a);
 }
 
 }  // namespace ggd

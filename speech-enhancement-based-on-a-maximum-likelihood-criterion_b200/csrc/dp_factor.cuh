@@ -9,8 +9,8 @@
 //   2. pushes that slice into every peer's arena with `factor_push_kernel` on a second stream the moment the producing
 //      GEMM has finished -- the transfer runs under the rest of the forward / backward chain (the push CTAs use no
 //      shared memory and co-reside with the GEMM CTAs) -- and raises a per-array flag at every peer,
-//   3. runs the gradient + momentum update REPLICATED over the whole minibatch (dw_wide.cu waits for the flags layer
-//      by layer, top layer first) and `bias_wide_kernel` for the biases.
+//   3. runs the gradient + momentum update (weights and biases) REPLICATED over the whole minibatch (dw_wide.cu waits for
+//      the flags layer by layer, top layer first).
 // Every rank computes the same sums in the same order: weights stay bit-identical without ever being exchanged, and
 // ggd_get_weights needs no gather.  The per-dimension sum_m|e|^beta of the GGD scale is exchanged the same way inside
 // the loss epilogue (gemm_tc.cu) / loss_kernel mode 3, so alpha equals the unsharded minibatch's on every rank.
@@ -23,7 +23,7 @@
 
 namespace ggd {
 
-constexpr int FX_TRACE_WIDE = 4 * FX_STRIDE, FX_TRACE_BIAS = FX_TRACE_WIDE + 16, FX_TRACE_WORDS = FX_TRACE_BIAS + 4;
+constexpr int FX_TRACE_WIDE = 4 * FX_STRIDE, FX_TRACE_WORDS = FX_TRACE_WIDE + 16;
 
 struct FxSeg {
     const uint8_t *src;          // local source (my slice)
@@ -49,26 +49,5 @@ struct FxPushArgs {
     unsigned long long *trace;            // optional globaltimer stamps [event*4 + {start, waited, copied, flagged}] (GGD_FX_TRACE=1)
 };
 void launch_factor_push(const FxPushArgs &a, int grid, cudaStream_t s);
-
-// bias gradients over the WHOLE minibatch + bias update of all layers (kernAccSumrow, DevFunc.cu:267-285; BP_GPU.cu:434-437)
-struct BiasWideLayer {
-    const bf16 *hi, *lo;   // dE/dx over the whole minibatch [rows][ld]
-    int ld, N;
-    float *b, *db;
-    int ev_dx;             // flag to wait for (world > 1), else -1
-};
-struct BiasWideArgs {
-    BiasWideLayer layer[10];
-    int nlayers, rows;     // rows = frames of the whole (padded) minibatch; padding rows are zero
-    float mom, lr, Mg;
-    int world, rank;
-    const unsigned int *flags;
-    unsigned int *bias_step;     // completed bias steps (own counter: this kernel runs beside dw_wide)
-    unsigned int *block_counter;
-    unsigned int *error_flag;
-    unsigned int *hang;
-    unsigned long long *trace;   // optional: [FX_TRACE_BIAS + {start, end}]
-};
-void launch_bias_wide(const BiasWideArgs &a, cudaStream_t s);
 
 }  // namespace ggd

@@ -23,8 +23,8 @@
 //               delta <- mom*delta - lr*(g/Mg + wc*W), W <- W + delta, written back in place
 //   warp 10     store warp: TMA stores of W and delta, releases the stage once the store engine has read it
 //   warp 11     weight producer: fp32 W and delta quarter tiles by TMA, running ahead of the update by the ring depth
-// All global traffic is TMA.  HBM bytes: 16 B/param (read W, delta; write W, delta).  The bias gradients + bias update
-// are a separate small kernel on a second stream (dp_factor.cu: bias_wide_kernel).
+// All weight traffic is TMA.  HBM bytes: 16 B/param (read W, delta; write W, delta).  The bias gradients + bias update are the
+// kernel's tail: every CTA that has finished its slabs sums its share of the dE/dx columns over the whole minibatch.
 #include "dp_factor.cuh"
 #include "pipe.cuh"
 #include "../../include/ggd_train.h"
@@ -41,7 +41,7 @@ constexpr int OP_STAGE = 2 * A_PART + 2 * B_PART;  // 48 KB
 constexpr int WD_ROWS = 16;
 constexpr int WD_F32 = WD_ROWS * TN * 4;           // 8 KB: 16 k x 128 n fp32
 constexpr int WD_STAGE = 2 * WD_F32;               // W + delta
-constexpr int MAX_OPS = 3, MAX_WDS = 8;
+constexpr int MAX_OPS = 4, MAX_WDS = 8;
 constexpr int NTHREADS = 384;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
@@ -311,6 +311,48 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
+    // ===== biases (kernAccSumrow + updatedelta + DevAccSum, DevFunc.cu:267-285; BP_GPU.cu:434-437): column sums of dE/dx over the
+    // WHOLE minibatch in a fixed order (identical on every rank), 32 columns per item, items dealt round-robin to the CTAs.
+    // Done HERE, by the CTAs that have finished their slabs, rather than by a kernel of its own: a second kernel spinning on the
+    // peers' flags can fill the SMs and starve the very push kernels the peers are waiting for (a real deadlock in eager mode).
+    {
+        float(*red)[33] = reinterpret_cast<float(*)[33]>(smem);     // the pipeline has drained: 12 x 33 floats of the ring
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 columns x 12 row lanes
+        const unsigned int step = gp->world > 1 ? *gp->step_counter + 1u : 0u;
+        int item = 0;
+        for (int li = 0; li < gp->nlayers; li++) {
+            const DwwLayer *L = &gp->layer[li];
+            const int nblk = (L->N + 31) / 32;
+            bool mine = false;
+            for (int bk = 0; bk < nblk; bk++) mine |= ((item + bk) % (int)gridDim.x) == (int)blockIdx.x;
+            if (mine && gp->world > 1) {
+                if (threadIdx.x == 0) wide_wait_flags(gp, L->ev_dx, step);     // (long since raised; CTAs without slabs in this layer never looked)
+                __syncthreads();
+            }
+            for (int bk = 0; bk < nblk; bk++, item++) {
+                if (item % (int)gridDim.x != (int)blockIdx.x) continue;
+                const int n = bk * 32 + tx;
+                float sacc = 0.0f;
+                if (n < L->N)
+                    for (int m = ty; m < gp->rows; m += NTHREADS / 32) {
+                        const unsigned short hv = __ldcg(reinterpret_cast<const unsigned short *>(L->dx_hi) + (size_t)m * L->Np + n);
+                        const unsigned short lv = __ldcg(reinterpret_cast<const unsigned short *>(L->dx_lo) + (size_t)m * L->Np + n);
+                        sacc += __uint_as_float((unsigned int)hv << 16) + __uint_as_float((unsigned int)lv << 16);
+                    }
+                red[ty][tx] = sacc;
+                __syncthreads();
+                if (ty == 0 && n < L->N) {
+                    float g = red[0][tx];
+#pragma unroll
+                    for (int r = 1; r < NTHREADS / 32; r++) g += red[r][tx];
+                    const float db = gp->mom * L->db[n] - gp->lr * (g / gp->Mg);   // no weight cost on biases (BP_GPU.cu:435)
+                    L->db[n] = db;
+                    L->b[n] = db + L->b[n];
+                }
+                __syncthreads();
+            }
+        }
+    }
     // last CTA out: the device-side bunch counter moves on; in data-parallel mode the step counter too, and every peer
     // learns that this rank no longer reads its factor arena (the peers' next pushes wait for that)
     if (threadIdx.x == 0 && gp->advance) {
@@ -325,7 +367,7 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
                 *gp->step_counter = step;
                 __threadfence_system();
                 for (int p = 0; p < gp->world; p++)
-                    if (p != gp->rank) st_release_sys_u32(gp->peer_flags[p] + gp->rank * FX_STRIDE + FX_EV_DONE, step);
+                    if (p != gp->rank) st_relaxed_sys_u32(gp->peer_flags[p] + gp->rank * FX_STRIDE + FX_EV_DONE, step);
             }
         }
     }
@@ -333,11 +375,13 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
 
 int dw_wide_smem(int fblocks, int *op_stages, int *wd_stages)
 {
-    // long frame loops are tensor / L2-fabric bound (deep operand ring); short ones are HBM bound (deep weight ring)
-    int ops = fblocks >= 16 ? 3 : 2;
-    int wds = (int)((208 * 1024 - ops * dww::OP_STAGE) / dww::WD_STAGE);
+    // Both streams are latency bound (bytes in flight per SM / round trip): the operand stream needs FB stages per segment at
+    // ~1.9 us per ring round, the weight stream 204 MB through (stages x 16 KB) per ~2 us.  Measured on B200: 128-256 frames
+    // are HBM bound (deep weight ring), 1024 frames operand bound (deep operand ring).
+    int ops = fblocks >= 32 ? 4 : (fblocks >= 16 ? 3 : 2);
+    int wds = (int)((224 * 1024 - ops * dww::OP_STAGE) / dww::WD_STAGE);
     if (wds > dww::MAX_WDS) wds = dww::MAX_WDS;
-    { const char *ev = getenv("GGD_WIDE_OPS"); if (ev && atoi(ev) >= 2 && atoi(ev) <= dww::MAX_OPS) { ops = atoi(ev); wds = (int)((208 * 1024 - ops * dww::OP_STAGE) / dww::WD_STAGE); if (wds > dww::MAX_WDS) wds = dww::MAX_WDS; } }
+    { const char *ev = getenv("GGD_WIDE_OPS"); if (ev && atoi(ev) >= 2 && atoi(ev) <= dww::MAX_OPS) { ops = atoi(ev); wds = (int)((224 * 1024 - ops * dww::OP_STAGE) / dww::WD_STAGE); if (wds > dww::MAX_WDS) wds = dww::MAX_WDS; } }
     if (wds < 2) wds = 2;
     *op_stages = ops; *wd_stages = wds;
     return ops * dww::OP_STAGE + wds * dww::WD_STAGE + 1024;
@@ -360,7 +404,7 @@ int launch_dw_wide(const DwwArgs *dev_args, int grid, int smem_bytes, cudaStream
 
 int dw_wide_init()
 {
-    GGD_CUDA(cudaFuncSetAttribute(dw_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 209 * 1024));
+    GGD_CUDA(cudaFuncSetAttribute(dw_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     return GGD_OK;
 }
 

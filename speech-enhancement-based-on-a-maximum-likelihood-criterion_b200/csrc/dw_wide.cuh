@@ -16,6 +16,9 @@ struct DwwLayer {
     int n_slabs;              // slabs of this layer: ceil(Np / 128) * k_slabs
     int b_rows_from_ctl;      // add ctl->bunch_idx * rows_per_bunch to the frame coordinate of b_hi / b_lo (one GPU, layer 1)
     int ev_dx, ev_y;          // data parallel: flags that every peer must have raised before the operands are read (-1: none)
+    const bf16 *dx_hi, *dx_lo; // the same dE/dx arrays as a_hi / a_lo (pitch Np), for the bias gradient
+    float *b, *db;            // bias and its momentum
+    int N;                    // real output units
     float wc;
 };
 struct DwwArgs {
@@ -24,6 +27,7 @@ struct DwwArgs {
     StepCtl *ctl;
     int rows_per_bunch;
     int fblocks;              // frames of the whole (padded) minibatch / 32
+    int rows;                 // = 32 * fblocks
     int op_stages, wd_stages; // ring depths (dw_wide_smem)
     float mom, lr, Mg;
     int advance;              // last CTA out increments ctl->bunch_idx (and the data-parallel step counter)

@@ -196,7 +196,7 @@ __device__ __forceinline__ void epilogue_loss16(const GemmArgs &g, int i, int j,
             __syncwarp(0x0000ffffu);
             if (t == 0)
                 for (int pr = 0; pr < g.world; pr++)
-                    if (pr != g.rank) st_release_sys_u32(g.lflags[pr] + g.rank * FX_STRIDE + FX_EV_LOSS + chunk, step);
+                    if (pr != g.rank) st_relaxed_sys_u32(g.lflags[pr] + g.rank * FX_STRIDE + FX_EV_LOSS + chunk, step);   // (fenced above)
             if (t < g.world && t != g.rank) {
                 const unsigned int *f = g.lflags[g.rank] + t * FX_STRIDE + FX_EV_LOSS + chunk;
                 const long long t0 = clock64();

@@ -54,7 +54,7 @@ constexpr int HANG_WORDS = 8 + 160 * 12 * 4;
 constexpr int FX_NEVENTS = 64;      // fork / join events of one step
 constexpr int FX_NSIDE = 12;        // side streams: every factor push (and the bias update) is its own branch of the step graph
 // fx_counters words
-constexpr int FXC_STEP = 0, FXC_BIAS_STEP = 1, FXC_BIAS_BLOCKS = 2, FXC_ERROR = 3, FXC_PUSH_BLOCKS = 8, FXC_WORDS = 8 + FX_STRIDE;
+constexpr int FXC_STEP = 0, FXC_ERROR = 3, FXC_PUSH_BLOCKS = 8, FXC_WORDS = 8 + FX_STRIDE;
 
 struct LayerInfo {
     int prev, cur;      // real units
@@ -106,11 +106,10 @@ struct ggd_handle {
     bool w_f32;         // GEMMs read the fp32 master weights and split them in-kernel: no bf16 weight shadows are maintained
     bool fused;         // gradient GEMM + update fused (tensor path; one GPU or factor-exchange data parallelism)
     bool persist;       // fused, one GPU, the bunch is one reduction tile: dw_persist.cu
-    bool wide;          // fused, any other case: dw_wide.cu + bias_wide_kernel
+    bool wide;          // fused, any other case: dw_wide.cu (weights and biases)
     DwpArgs *dwp_dev;   // argument block of dw_persist (device memory)
     DwwArgs *dww_dev;   // argument block of dw_wide (device memory)
     int wide_smem;
-    BiasWideArgs bias_wide;
     unsigned int *dwp_counter;
     unsigned int *hang_host, *hang_dev;   // host-mapped record written by a device-side watchdog before it traps
     cudaGraphExec_t g1, gN;
@@ -341,10 +340,11 @@ static int build_plans(ggd_handle *h)
             d.b_rows_from_ctl = in_chunk;
             d.ev_dx = h->dp_fx ? FX_EV_DX + l : -1; d.ev_y = h->dp_fx ? FX_EV_Y + (l - 1) : -1;
             d.wc = h->cfg.weightcost;
+            d.dx_hi = h->dx_hi[l]; d.dx_lo = h->dx_lo[l]; d.b = h->P + ly.b_off; d.db = h->Dl + ly.b_off; d.N = ly.cur;
             base += ceil_div(ly.Np, 128) * d.k_slabs;
         }
         a->total_slabs = base;
-        a->ctl = h->ctl; a->rows_per_bunch = h->M; a->fblocks = h->fx_rows / 32;
+        a->ctl = h->ctl; a->rows_per_bunch = h->M; a->fblocks = h->fx_rows / 32; a->rows = h->fx_rows;
         h->wide_smem = dw_wide_smem(a->fblocks, &a->op_stages, &a->wd_stages);
         a->mom = h->cfg.momentum; a->lr = h->cfg.lrate; a->Mg = (float)h->Mg;
         a->advance = 1; a->done_counter = h->dwp_counter; a->hang = h->hang_dev;
@@ -359,21 +359,6 @@ static int build_plans(ggd_handle *h)
         delete a;
         GGD_TRY(rc);
         GGD_CUDA(e);
-        // biases: column sums of dE/dx over the whole minibatch, beside the weight kernel
-        BiasWideArgs &b = h->bias_wide;
-        memset(&b, 0, sizeof b);
-        for (int l = L - 1; l >= 1; l--) {
-            const LayerInfo &ly = h->lay[l];
-            BiasWideLayer &bl = b.layer[b.nlayers++];
-            bl.hi = h->dx_hi[l]; bl.lo = h->dx_lo[l]; bl.ld = ly.Np; bl.N = ly.cur;
-            bl.b = h->P + ly.b_off; bl.db = h->Dl + ly.b_off;
-            bl.ev_dx = h->dp_fx ? FX_EV_DX + l : -1;
-        }
-        b.rows = h->fx_rows; b.mom = h->cfg.momentum; b.lr = h->cfg.lrate; b.Mg = (float)h->Mg;
-        b.world = world; b.rank = rank; b.hang = h->hang_dev;
-        b.flags = h->fx_flags;
-        b.trace = h->fx_trace;
-        b.bias_step = h->fx_counters + FXC_BIAS_STEP; b.block_counter = h->fx_counters + FXC_BIAS_BLOCKS; b.error_flag = h->fx_counters + FXC_ERROR;
     }
     if (h->dp_fx) {
         // one push per factor array: my slice -> the same rows of every peer's arena
@@ -464,7 +449,7 @@ static int dp_fx_setup(ggd_handle *h)
     GGD_CUDA(cudaMemset(h->fx_flags, 0, (size_t)FX_MAX * FX_STRIDE * sizeof(unsigned int)));
     void *local[3] = {h->fx_arena, h->fx_asum, h->fx_flags};
     GGD_TRY(ipc_exchange(h, local, 3, h->fx_peer));
-    { const char *ev = getenv("GGD_FX_PUSH_CTAS"); h->fx_push_ctas = (ev && atoi(ev) > 0) ? atoi(ev) : 32 + 16 * (world - 2); }   // 32 CTAs per peer-MB is ample
+    { const char *ev = getenv("GGD_FX_PUSH_CTAS"); h->fx_push_ctas = (ev && atoi(ev) > 0) ? atoi(ev) : 32 + 4 * (world - 2); }   // 32 CTAs per peer-MB is ample
     GGD_TRY(dp_barrier(h));    // nobody may enter the first step before every rank has mapped everyone
     return GGD_OK;
 }
@@ -589,10 +574,7 @@ static int enqueue_step(ggd_handle *h, cudaStream_t s, bool apply_update, int *l
         return GGD_OK;
     }
     if (fused && h->wide) {
-        // biases on the side stream (small, latency-bound) beside the persistent weight kernel; both close the step
-        cudaStream_t side;
-        GGD_TRY(fx_fork(h, s, &sc, &side));
-        { ProfScope ps(h, KC_BIAS, side); launch_bias_wide(h->bias_wide, side); (*launches)++; }
+        // weights, biases and the bunch counter of the whole (global) minibatch: one persistent launch
         { ProfScope ps(h, KC_DWUPD, s); GGD_TRY(launch_dw_wide(h->dww_dev, h->sm_count, h->wide_smem, s)); (*launches)++; }
         GGD_TRY(fx_join(h, s, &sc));
         GGD_CUDA(cudaGetLastError());
@@ -786,7 +768,7 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
             if (tr[ev * 4]) { snprintf(buf, sizeof buf, "push%d[start %.1f waited %.1f copied %.1f flagged %.1f] ", ev, us(ev * 4), us(ev * 4 + 1), us(ev * 4 + 2), us(ev * 4 + 3)); line += buf; }
         snprintf(buf, sizeof buf, "wide[start %.1f pdl %.1f", us(FX_TRACE_WIDE), us(FX_TRACE_WIDE + 1)); line += buf;
         for (int l = 0; l < 10; l++) if (tr[FX_TRACE_WIDE + 2 + l]) { snprintf(buf, sizeof buf, " ready%d %.1f", l, us(FX_TRACE_WIDE + 2 + l)); line += buf; }
-        snprintf(buf, sizeof buf, " end %.1f] bias[start %.1f end %.1f]", us(FX_TRACE_WIDE + 14), us(FX_TRACE_BIAS), us(FX_TRACE_BIAS + 1)); line += buf;
+        snprintf(buf, sizeof buf, " end %.1f]", us(FX_TRACE_WIDE + 14)); line += buf;
         fprintf(stderr, "%s\n", line.c_str());
         GGD_CUDA(cudaMemset(h->fx_trace, 0, FX_TRACE_WORDS * 8));
     }
@@ -1082,16 +1064,13 @@ int ggd_train_device(ggd_handle *h, int n_frames, const float *d_in, const float
     return run_chunk(h, n_frames, d_in, d_targ);
 }
 
-// forward-only over n frames in bunches of M (a partial last bunch IS processed: BP_GPU.cu:203-218)
-static int forward_chunk(ggd_handle *h, int n_frames, const float *in)
+// forward-only over the n frames whose net input is already in the chunk arrays (c_in, or c_hi / c_lo on the tensor path),
+// in bunches of M (a partial last bunch IS processed: BP_GPU.cu:203-218); the outputs land in c_out and in h_out
+static int forward_resident(ggd_handle *h, int n_frames, bool denorm = false, const float *d_mean = nullptr, const float *d_dvar = nullptr, int fea_dim = 0)
 {
-    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
-    GGD_TRY(ensure_chunk(h, n_frames));
     const int D = h->units[h->L - 1], ldo = h->upad[h->L - 1];
-    GGD_TRY(upload(h, in, h->c_in, (size_t)n_frames * h->units[0] * sizeof(float)));
     GGD_TRY(set_ctl(h, h->c_in, h->c_targ));
     const int nb = ceil_div(n_frames, h->M);
-    if (h->tensor) launch_split_rows(h->c_in, n_frames, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main);
     int launches = 0;
     for (int b = 0; b < nb; b++) {
         const int f = (n_frames - b * h->M < h->M) ? n_frames - b * h->M : h->M;
@@ -1100,10 +1079,20 @@ static int forward_chunk(ggd_handle *h, int n_frames, const float *in)
                                    cudaMemcpyDeviceToDevice, h->s_main));
         launch_advance(h->ctl, h->s_main);
     }
+    if (denorm) launch_denorm(h->c_out, n_frames, D, d_mean, d_dvar, fea_dim, h->s_main);
     h->h_out.resize((size_t)n_frames * D);
     GGD_CUDA(cudaMemcpyAsync(h->h_out.data(), h->c_out, (size_t)n_frames * D * sizeof(float), cudaMemcpyDeviceToHost, h->s_main));
     GGD_CUDA(cudaStreamSynchronize(h->s_main));
     return GGD_OK;
+}
+
+static int forward_chunk(ggd_handle *h, int n_frames, const float *in)
+{
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    GGD_TRY(upload(h, in, h->c_in, (size_t)n_frames * h->units[0] * sizeof(float)));
+    if (h->tensor) launch_split_rows(h->c_in, n_frames, h->units[0], h->c_hi, h->c_lo, h->upad[0], h->s_main);
+    return forward_resident(h, n_frames);
 }
 
 int ggd_forward(ggd_handle *h, int n_frames, const float *in, float *out)
@@ -1115,15 +1104,29 @@ int ggd_forward(ggd_handle *h, int n_frames, const float *in, float *out)
 }
 
 // The three CV metrics accumulate on the host in float, frame-major order, exactly like the reference.
-int ggd_cv_sqerr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result)
+static float metric_sqerr(const ggd_handle *h, int n_frames, const float *targ)
 {
-    if (!h || !in || !targ || !result) { set_error("ggd_cv_sqerr: bad argument"); return GGD_EINVAL; }
-    GGD_TRY(forward_chunk(h, n_frames, in));
     const size_t n = (size_t)n_frames * h->units[h->L - 1];
     const float *o = h->h_out.data();
     float s = 0.0f;
     for (size_t i = 0; i < n; i++) s = s + (o[i] - targ[i]) * (o[i] - targ[i]);   // BP_GPU.cu:211
-    *result = s;
+    return s;
+}
+static float metric_abserr(const ggd_handle *h, int n_frames, const float *targ)
+{
+    const int D = h->units[h->L - 1];
+    const size_t n = (size_t)n_frames * D;
+    const float *o = h->h_out.data();
+    float s = 0.0f;
+    for (size_t i = 0; i < n; i++) s = s + fabsf(o[i] - targ[i]);                  // BP_GPU.cu:244
+    return s / D;                                                                  // BP_GPU.cu:250
+}
+
+int ggd_cv_sqerr(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result)
+{
+    if (!h || !in || !targ || !result) { set_error("ggd_cv_sqerr: bad argument"); return GGD_EINVAL; }
+    GGD_TRY(forward_chunk(h, n_frames, in));
+    *result = metric_sqerr(h, n_frames, targ);
     return GGD_OK;
 }
 
@@ -1131,12 +1134,7 @@ int ggd_cv_abserr(ggd_handle *h, int n_frames, const float *in, const float *tar
 {
     if (!h || !in || !targ || !result) { set_error("ggd_cv_abserr: bad argument"); return GGD_EINVAL; }
     GGD_TRY(forward_chunk(h, n_frames, in));
-    const int D = h->units[h->L - 1];
-    const size_t n = (size_t)n_frames * D;
-    const float *o = h->h_out.data();
-    float s = 0.0f;
-    for (size_t i = 0; i < n; i++) s = s + fabsf(o[i] - targ[i]);                  // BP_GPU.cu:244
-    *result = s / D;                                                               // BP_GPU.cu:250
+    *result = metric_abserr(h, n_frames, targ);
     return GGD_OK;
 }
 
@@ -1166,10 +1164,57 @@ static float gamma_ref(float x)   // BP_GPU::Gamma, BP_GPU.cu:593-640
     return 0;
 }
 
+static int metric_loglik(ggd_handle *h, int n_frames, const float *targ, float *result);
+
 int ggd_cv_loglik(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result)
 {
     if (!h || !in || !targ || !result) { set_error("ggd_cv_loglik: bad argument"); return GGD_EINVAL; }
     GGD_TRY(forward_chunk(h, n_frames, in));
+    return metric_loglik(h, n_frames, targ, result);
+}
+
+int ggd_cv_all(ggd_handle *h, int n_frames, const float *in, const float *targ, float *result3)
+{
+    if (!h || !in || !targ || !result3) { set_error("ggd_cv_all: bad argument"); return GGD_EINVAL; }
+    GGD_TRY(forward_chunk(h, n_frames, in));          // ONE forward pass feeds the three metrics (the reference runs it three times)
+    result3[0] = metric_sqerr(h, n_frames, targ);
+    result3[1] = metric_abserr(h, n_frames, targ);
+    result3[2] = 0.0f;
+    if (h->cfg.MLflag == 1) GGD_TRY(metric_loglik(h, n_frames, targ, &result3[2]));
+    return GGD_OK;
+}
+
+int ggd_enhance(ggd_handle *h, int n_frames, const float *lps, int fea_dim, int fea_context, const float *mean, const float *dvar, float *out)
+{
+    if (!h || !lps || !mean || !dvar || !out || n_frames < 0) { set_error("ggd_enhance: bad argument"); return GGD_EINVAL; }
+    const int D = h->units[h->L - 1];
+    if (fea_dim < 1 || fea_context < 1 || (fea_context & 1) == 0 || fea_dim * fea_context != h->units[0]) {
+        set_error("ggd_enhance: fea_dim %d x fea_context %d (odd) must equal layersizes[0] %d", fea_dim, fea_context, h->units[0]); return GGD_EINVAL;
+    }
+    if (n_frames > GGD_MAXCACHEFRAME) { set_error("n_frames %d exceeds MAXCACHEFRAME %d", n_frames, GGD_MAXCACHEFRAME); return GGD_EINVAL; }
+    if (n_frames == 0) return GGD_OK;
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    GGD_TRY(ensure_chunk(h, n_frames));
+    // raw features + norm constants ride in the loader's staging buffers
+    GGD_TRY(grow(&h->r_fea, &h->r_cap_fea, (size_t)n_frames * fea_dim));
+    GGD_TRY(grow(&h->r_norm, &h->r_cap_norm, (size_t)2 * fea_dim));
+    float *d_lps = reinterpret_cast<float *>(h->r_fea);
+    GGD_CUDA(cudaMemcpyAsync(d_lps, lps, (size_t)n_frames * fea_dim * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->r_norm, mean, (size_t)fea_dim * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    GGD_CUDA(cudaMemcpyAsync(h->r_norm + fea_dim, dvar, (size_t)fea_dim * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
+    EdgeExpandArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.lps = d_lps; ea.mean = h->r_norm; ea.dvar = h->r_norm + fea_dim; ea.frames = n_frames; ea.fea_dim = fea_dim; ea.ctx = fea_context;
+    ea.in32 = h->tensor ? nullptr : h->c_in; ea.in_hi = h->tensor ? h->c_hi : nullptr; ea.in_lo = h->tensor ? h->c_lo : nullptr; ea.ld = h->upad[0];
+    launch_expand_edges(ea, h->s_main);
+    GGD_CUDA(cudaGetLastError());
+    GGD_TRY(forward_resident(h, n_frames, true, h->r_norm, h->r_norm + fea_dim, fea_dim));
+    memcpy(out, h->h_out.data(), (size_t)n_frames * D * sizeof(float));
+    return GGD_OK;
+}
+
+static int metric_loglik(ggd_handle *h, int n_frames, const float *targ, float *result)
+{
     const int D = h->units[h->L - 1];
     std::vector<float> al(D);
     GGD_CUDA(cudaMemcpy(al.data(), h->alpha, D * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1301,6 +1346,7 @@ int ggd_profile_kernels(ggd_handle *h, int n_frames, const float *d_in, const fl
     const int nb = n_frames / h->M;
     memset(out, 0, sizeof *out);
     if (nb == 0) return GGD_OK;
+    if (h->has_comm) GGD_TRY(dp_barrier(h));
     GGD_TRY(set_ctl(h, d_in, d_targ));
     GGD_CUDA(cudaMemsetAsync(h->trace, 0, h->trace_cap * sizeof(double), h->s_main));
     h->prof_on = true;
@@ -1309,6 +1355,12 @@ int ggd_profile_kernels(ggd_handle *h, int n_frames, const float *d_in, const fl
     for (int b = 0; b < nb && rc == GGD_OK; b++) rc = enqueue_step(h, h->s_main, true, &launches);
     h->prof_on = false;
     if (rc == GGD_OK) rc = sync_main(h);
+    else if (h->hang_host && h->hang_host[0] == 0xDEADu) {
+        // a device-side watchdog fired while launches were still being queued: say which one
+        const unsigned int *r = h->hang_host;
+        std::string prev = ggd_last_error();
+        set_error("%s [device watchdog: wait code %u gave up in block %u at iteration %u (parity/peer %u, thread %u)]", prev.c_str(), r[1], r[2], r[3], r[4], r[5]);
+    }
     for (size_t i = 0; i < h->prof_cls.size(); i++) {
         float ms = 0;
         cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]);

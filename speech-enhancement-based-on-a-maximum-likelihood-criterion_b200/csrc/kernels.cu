@@ -75,6 +75,51 @@ __global__ void __launch_bounds__(256) expand_chunk_kernel(const ExpandArgs a)
     }
 }
 
+__global__ void __launch_bounds__(256) expand_edges_kernel(const EdgeExpandArgs a)
+{
+    const int t = blockIdx.x, half = (a.ctx - 1) / 2;
+    const int in_dim = a.fea_dim * a.ctx;
+    for (int e = threadIdx.x; e < a.ld; e += blockDim.x) {
+        float v = 0.0f;
+        if (e < in_dim) {
+            const int c = e / a.fea_dim, j = e - c * a.fea_dim;
+            int f = t + c - half;                                   // frame_expand.m:8-23: left context, centre, right context
+            f = f < 0 ? 0 : (f > a.frames - 1 ? a.frames - 1 : f);  // edges replicate the first / last frame
+            v = __fmul_rn(__fsub_rn(__ldg(a.lps + (size_t)f * a.fea_dim + j), __ldg(a.mean + j)), __ldg(a.dvar + j));   // decode.m:31-33
+            if (a.in32) a.in32[(size_t)t * in_dim + e] = v;
+        }
+        if (a.in_hi) {
+            bf16 h, l;
+            split_bf16(v, h, l);
+            a.in_hi[(size_t)t * a.ld + e] = h;
+            a.in_lo[(size_t)t * a.ld + e] = l;
+        }
+    }
+}
+
+void launch_expand_edges(const EdgeExpandArgs &a, cudaStream_t s)
+{
+    if (a.frames <= 0) return;
+    expand_edges_kernel<<<a.frames, 256, 0, s>>>(a);
+}
+
+__global__ void denorm_kernel(float *out, long long n, int D, const float *mean, const float *dvar, int fea_dim)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % D) % fea_dim;
+        out[i] = __fadd_rn(__fdiv_rn(out[i], __ldg(dvar + k)), __ldg(mean + k));
+    }
+}
+
+void launch_denorm(float *out, long long frames, int D, const float *mean, const float *dvar, int fea_dim, cudaStream_t s)
+{
+    const long long n = frames * D;
+    if (n <= 0) return;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    denorm_kernel<<<(int)blocks, 256, 0, s>>>(out, n, D, mean, dvar, fea_dim);
+}
+
 void launch_expand_chunk(const ExpandArgs &a, cudaStream_t s)
 {
     if (a.samples <= 0) return;
@@ -152,7 +197,7 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
                     __syncwarp();
                     if (tx == 0)
                         for (int p = 0; p < a.world; p++)
-                            if (p != a.rank) st_release_sys_u32(a.lflags[p] + a.rank * FX_STRIDE + FX_EV_LOSS + blockIdx.x, step);
+                            if (p != a.rank) st_relaxed_sys_u32(a.lflags[p] + a.rank * FX_STRIDE + FX_EV_LOSS + blockIdx.x, step);   // (fenced above)
                     if (tx < a.world && tx != a.rank) {
                         const unsigned int *f = a.lflags[a.rank] + tx * FX_STRIDE + FX_EV_LOSS + blockIdx.x;
                         const long long t0 = clock64();

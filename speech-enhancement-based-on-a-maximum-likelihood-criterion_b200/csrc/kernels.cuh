@@ -46,6 +46,20 @@ struct ExpandArgs {
 };
 void launch_expand_chunk(const ExpandArgs &a, cudaStream_t s);
 
+// Inference-side input builder (Test_code/decode.m:28-34 + frame_expand.m:6-25): z-score of the raw LPS frames with the .norm
+// constants, then per frame t the context frames t-c..t+c with the utterance's first / last frame replicated at the edges.
+struct EdgeExpandArgs {
+    const float *lps;            // [frames][fea_dim] raw (un-normalised) features of ONE utterance
+    const float *mean, *dvar;    // [fea_dim]
+    int frames, fea_dim, ctx;
+    float *in32;                 // [frames][fea_dim*ctx] fp32 (validation path) or NULL
+    bf16 *in_hi, *in_lo;         // [frames][ld] (tensor path) or NULL
+    int ld;
+};
+void launch_expand_edges(const EdgeExpandArgs &a, cudaStream_t s);
+// out[f][d] = out[f][d] / dvar[d % fea_dim] + mean[d % fea_dim]   (decode.m:60-62)
+void launch_denorm(float *out, long long frames, int D, const float *mean, const float *dvar, int fea_dim, cudaStream_t s);
+
 struct LossArgs {
     const StepCtl *ctl;
     const float *out;   // [M][ldo] network output of this bunch (fp32)

@@ -5,8 +5,8 @@
 
 namespace ggd {
 
-// Bounded mbarrier wait: a pipeline bug must surface as an error, never as a hung GPU.  After ~2^22 failed probes
-// (seconds) the waiter records {code, block, iteration, parity} in host-mapped memory and traps.
+// Bounded mbarrier wait: a pipeline bug must surface as an error, never as a hung GPU.  After ~8.7 s of failed probes
+// the waiter records {code, block, iteration, parity} in host-mapped memory and traps.
 static __device__ __noinline__ void hang_report(unsigned int *rec, int code, int it, uint32_t parity)
 {
     if (rec) {
@@ -22,6 +22,7 @@ static __device__ __noinline__ void hang_report(unsigned int *rec, int code, int
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_saddr, uint32_t parity, unsigned int *rec, int code, int it)
 {
     unsigned int spins = 0;
+    const long long t0 = clock64();
     for (;;) {
         uint32_t ok;
         asm volatile(
@@ -38,7 +39,9 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_saddr, uint32_t 
             w[0] = (unsigned int)code; w[1] = (unsigned int)it; w[2] = parity; w[3] = 1;
             __threadfence_system();
         }
-        if (spins > (1u << 22)) hang_report(rec, code, it, parity);
+        // time based (~8.7 s at 1.97 GHz): LONGER than the 4.4 s a data-parallel kernel may legitimately wait for a peer's
+        // flags (that wait reports the missing rank itself), so a slow peer is never mistaken for a pipeline bug
+        if ((spins & 1023u) == 0 && clock64() - t0 > (1ll << 34)) hang_report(rec, code, it, parity);
     }
 }
 static __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity, unsigned int *rec, int code, int it)
@@ -103,6 +106,12 @@ static __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.a
 static __device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// relaxed flag store: the caller has ALREADY issued one system-scope fence after the data stores (fence + relaxed store is a
+// release pattern); a st.release.sys per peer pays one NVLink round trip EACH (~5 us: 35-40 us to flag 7 peers)
+static __device__ __forceinline__ void st_relaxed_sys_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 static __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p)
 {

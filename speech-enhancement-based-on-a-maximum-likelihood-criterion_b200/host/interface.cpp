@@ -4,8 +4,34 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <unistd.h>
 
 namespace bphost {
+
+// bulk read of [off, off + bytes) with `threads` concurrent pread()s (page cache / NVMe queues are not saturated by one reader)
+static bool pread_parallel(int fd, void *buf, size_t bytes, off_t off, int threads)
+{
+    if (threads < 1) threads = 1;
+    const size_t piece = (bytes / threads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> ts;
+    std::vector<char> ok(threads, 1);
+    for (int t = 0; t < threads; t++) {
+        const size_t b0 = (size_t)t * piece, b1 = b0 + piece < bytes ? b0 + piece : bytes;
+        if (b0 >= bytes) break;
+        ts.emplace_back([=, &ok] {
+            size_t done = b0;
+            while (done < b1) {
+                const ssize_t r = pread(fd, (char *)buf + done, b1 - done, off + (off_t)done);
+                if (r <= 0) { ok[t] = 0; return; }
+                done += (size_t)r;
+            }
+        });
+    }
+    for (auto &th : ts) th.join();
+    for (char c : ok) if (!c) return false;
+    return true;
+}
 
 static inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
 
@@ -49,7 +75,17 @@ bool Host::init(int argc, char **argv)
         else if (k == "MLflag") p.MLflag = atoi(v.c_str());
         else if (k == "traincache") p.traincache = atoi(v.c_str());
         else if (k == "bunchsize") p.bunchsize = atoi(v.c_str());
-        else if (k == "gpu_used") p.gpu_used = atoi(v.c_str());
+        else if (k == "gpu_used") {                                             // a comma list selects data parallelism (extension)
+            p.gpus.clear();
+            size_t pos = 0;
+            while (pos <= v.size()) {
+                const size_t c = v.find(',', pos);
+                p.gpus.push_back(atoi(v.substr(pos, c == std::string::npos ? std::string::npos : c - pos).c_str()));
+                if (c == std::string::npos) break;
+                pos = c + 1;
+            }
+            p.gpu_used = p.gpus.empty() ? 0 : p.gpus[0];
+        }
         else if (k == "init_randem_seed") p.init_randem_seed = atoi(v.c_str());
         else if (k == "momentum") p.momentum = (float)atof(v.c_str());
         else if (k == "shapefactor") p.shapefactor = (float)atof(v.c_str());
@@ -74,6 +110,7 @@ bool Host::init(int argc, char **argv)
         else if (k == "precision") p.precision = (v == "fp32" || v == "1") ? 1 : 0;
         else if (k == "no_graph") p.no_graph = atoi(v.c_str());
         else if (k == "host_loader") p.host_loader = atoi(v.c_str());
+        else if (k == "read_threads") p.read_threads = atoi(v.c_str());
         // anything else (e.g. numlayers=) is silently ignored, as in the reference
     }
     if (!(fp_log = fopen(p.log_file.c_str(), "wt"))) { printf("can not open output log file: %s\n", p.log_file.c_str()); return false; }
@@ -312,15 +349,22 @@ int Host::read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<un
     for (int i = 0; i < samples; i++) order[i] = i;
     shuffle(order);                                                        // per-sample shuffle, :750-754
     first.assign(samples, 0);
+    // both streams at once, each with read_threads concurrent pread()s (the records of a chunk are contiguous in the pfile)
+    bool ok_stream[2] = {true, true};
+    std::thread readers[2];
     for (int stream = 0; stream < 2; stream++) {
         const int dim = stream == 0 ? fd : D;
         FILE *fp = stream == 0 ? fp_data : fp_targ;
         std::vector<unsigned> &raw = stream == 0 ? fea_rec : targ_rec;
         const long rec = 4L * (dim + 2);
-        if (fseek(fp, kPfileHeader + (long)chunk_st[idx] * rec, SEEK_SET) != 0) { logf("%s pfile cannot fseek to chunk %d.\n", stream ? "targ" : "data", idx); return -1; }
         raw.resize((size_t)need * (dim + 2));
-        if (fread(raw.data(), rec, need, fp) != (size_t)need) { logf("%s pfile short read in chunk %d.\n", stream ? "targ" : "data", idx); return -1; }
+        readers[stream] = std::thread([=, &raw, &ok_stream] {
+            ok_stream[stream] = pread_parallel(fileno(fp), raw.data(), (size_t)need * rec, (off_t)kPfileHeader + (off_t)chunk_st[idx] * rec, p.read_threads);
+        });
     }
+    for (auto &r : readers) r.join();
+    for (int stream = 0; stream < 2; stream++)
+        if (!ok_stream[stream]) { logf("%s pfile short read in chunk %d.\n", stream ? "targ" : "data", idx); return -1; }
     int cur_sent = (int)bswap32(fea_rec[0]);
     int processed = 0, cur_frame = chunk_st[idx], cur_sample = 0;
     while (processed != need) {

@@ -16,6 +16,7 @@ struct Params {                          // struct WorkPara, Interface.h:31-69
     std::string fea_file, norm_file, targ_file, outwts_file, log_file, initwts_file, train_sent_range, cv_sent_range;
     int fea_dim = 0, fea_context = 0, targ_offset = 0, dropoutflag = 0, MLflag = 0, traincache = 0, bunchsize = 0;
     int gpu_used = 0, init_randem_seed = 0;
+    std::vector<int> gpus;      // gpu_used=0,1,2,3 (extension): frame-sharded data parallelism, one process per listed GPU
     float momentum = 0, shapefactor = 0, weightcost = 0, lrate = 0, visible_omit = 0, hid_omit = 0;
     float init_randem_weight_min = -0.1f, init_randem_weight_max = 0.1f, init_randem_bias_min = -0.1f, init_randem_bias_max = 0.1f;
     int numlayers = 0;
@@ -24,6 +25,7 @@ struct Params {                          // struct WorkPara, Interface.h:31-69
     int precision = 0;      // precision=fp32 selects the CUDA-core validation path
     int no_graph = 0;
     int host_loader = 0;    // host_loader=1: z-score / context expansion on the CPU (ggd_train) instead of the device-side loader
+    int read_threads = 4;   // read_threads=N: threads per pfile for the bulk record reads of the device-side loader
 };
 
 class Host {

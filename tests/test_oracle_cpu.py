@@ -370,3 +370,22 @@ def test_host_raw_chunk_reader(oracle, tmp_path, traincache):
         assert np.array_equal(first[:n], f0)
         assert np.array_equal(fea[:need.value, 2:], fr[:, 2:]) and np.array_equal(tg[:need.value, 2:], tr[:, 2:])
     L.bph_destroy(h)
+
+
+def test_frame_expand_matches_reference_loops():
+    """oracle.frame_expand against a literal transcription of the loops of Test_code/frame_expand.m:6-25 (1-based indices)"""
+    from oracle import oracle as O
+    rng = np.random.RandomState(0)
+    for T in (1, 2, 3, 9):
+        f = rng.randn(T, 4)
+        ctx = 7
+        rows = []
+        for t in range(1, T + 1):
+            parts = []
+            for c in range((ctx - 1) // 2, 0, -1):
+                parts.append(f[0] if t - c <= 0 else f[t - c - 1])
+            parts.append(f[t - 1])
+            for c in range(1, (ctx - 1) // 2 + 1):
+                parts.append(f[T - 1] if t + c >= T else f[t + c - 1])
+            rows.append(np.concatenate(parts))
+        assert np.array_equal(O.frame_expand(f, ctx), np.stack(rows))

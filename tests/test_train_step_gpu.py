@@ -309,3 +309,33 @@ def test_config4_shape_single_gpu(pkg, oracle, M):
         assert rel_err(Wg[l] - W[l], Wo[l] - W[l]) < 2e-3, "update of layer %d" % (l + 1)
         assert rel_err(bg[l] - b[l], bo[l] - b[l]) < 2e-3
     net.close()
+
+
+@pytest.mark.parametrize("precision,tol", [(1, 2e-5), (0, 1e-3)])
+def test_enhance_inference_path(pkg, oracle, precision, tol):
+    """ggd_enhance = Test_code/decode.m for one utterance (z-score, edge-replicated context of frame_expand.m, forward,
+    de-normalisation) against the float64 numpy restatement; utterances shorter than the context and longer than a bunch"""
+    O = oracle
+    layersizes, M = [7 * 33, 96, 80, 33], 128
+    W, b, _, _ = make_case(O, layersizes, M, 37)
+    rng = np.random.RandomState(3)
+    mean = rng.randn(33).astype(np.float32); dvar = rng.uniform(0.5, 2.0, 33).astype(np.float32)
+    net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1, precision=precision)
+    for T in (1, 2, 5, 128, 333):
+        lps = (rng.randn(T, 33) * 3 + 10).astype(np.float32)
+        got = net.enhance(lps, mean, dvar, 7)
+        ref = O.enhance_ref(lps, W, b, layersizes, mean, dvar, 7)
+        assert got.shape == ref.shape == (T, 33)
+        assert rel_err(got, ref) < tol, T
+    with pytest.raises(Exception):
+        net.enhance(np.zeros((4, 33), np.float32), mean, dvar, 5)      # 5 x 33 != layersizes[0]
+
+
+def test_cv_all_equals_three_calls(pkg, oracle):
+    O = oracle
+    layersizes, M = SMALL, 128
+    W, b, x, t = make_case(O, layersizes, 300, 43)
+    net = pkg.BP_GPU(0, 0, len(layersizes), layersizes, M, 0.1, 0.9, 1e-5, W, b, 1.5, 1)
+    net.train(256, x[:256], t[:256])            # sets alpha for CrossValid2
+    a = net.CrossValidAll(300, x, t)
+    assert a == (net.CrossValid(300, x, t), net.CrossValiddB(300, x, t), net.CrossValid2(300, x, t))
