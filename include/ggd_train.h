@@ -25,6 +25,7 @@
  */
 #ifndef GGD_TRAIN_H_
 #define GGD_TRAIN_H_
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -105,8 +106,20 @@ typedef struct ggd_raw_chunk {
     const int *sample_first_frame;       /* [n_samples], 0 <= f and f + fea_context <= n_frames */
     int fea_dim, fea_context, targ_offset;
     const float *mean, *dvar;            /* [fea_dim] */
+    /* Data parallelism: every rank may supply only ITS slice of the chunk's records and the library all-gathers them over
+     * NVLink (ncclAllGather) -- each pfile byte is then read from disk and crosses PCIe once per node instead of once per
+     * GPU.  rec_frames == 0: the arrays above hold all n_frames records.  Otherwise they hold the records of frames
+     * [rec_frame0, rec_frame0 + rec_frames) with rec_frame0 = rank * S, S = ceil(n_frames / world_size),
+     * rec_frames = min(S, n_frames - rec_frame0) (clamped at 0). */
+    int rec_frame0, rec_frames;
 } ggd_raw_chunk;
 int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *chunk);
+/* Page-locked host memory for chunk buffers (the record arrays of ggd_raw_chunk, the arrays of ggd_train): copies from it
+ * run at PCIe speed and overlap the training steps; pageable memory is staged by the driver at a fraction of that. */
+/* makes the handle's GPU the calling thread's current device (call it once in a loader thread before ggd_host_alloc) */
+int ggd_bind_thread(ggd_handle *h);
+void *ggd_host_alloc(size_t bytes);
+void ggd_host_free(void *p);
 
 /* Drops the GGD_FLAG_PIN_HOST registration of a host buffer previously passed to ggd_train (call it before freeing or
  * reallocating such a buffer while the handle lives; unknown pointers are ignored). */

@@ -16,9 +16,10 @@
  * lps_extract               main frame loop for one utterance (host buffers)
  * lps_extract_batch         the same for many utterances in one launch (host buffers)
  * lps_extract_batch_device  the same with device-resident PCM / features
- * Output options (flags) cover the two consumers of the features: the HTK writer
- * (big-endian floats, fileio.c:231-243) and the trainer's z-score with the reciprocal-std .norm
- * file (Interface.cc:760-766).
+ * lps_norm_reset/finalize     qnnorm (tools_pfile/get_norm.pl:4): mean / reciprocal std per bin, accumulated on the device
+ * Output options (flags) cover the consumers of the features: the HTK writer (big-endian floats,
+ * fileio.c:231-243), the trainer's z-score with the reciprocal-std .norm file (Interface.cc:760-766) and
+ * the pfile records feacat builds from the HTK files (tools_pfile/pfile_noisy.pl:33).
  */
 #ifndef LPS_B200_H_
 #define LPS_B200_H_
@@ -34,6 +35,11 @@ extern "C" {
 enum {
     LPS_FLAG_BIG_ENDIAN = 1,  /* byte-swap each float (ready for fwrite into an HTK file) */
     LPS_FLAG_ZSCORE = 2,      /* (x - mean[k]) * dvar[k] with the .norm constants; not combinable with BIG_ENDIAN */
+    LPS_FLAG_PFILE = 8,       /* write QuickNet pfile RECORDS instead of bare features: per frame 259 big-endian words {sentence index,
+                                 frame index in the sentence, 257 float32} -- the payload feacat produces (tools_pfile/pfile_noisy.pl:33),
+                                 ready to be written after the 32 768-byte header.  `out` must hold frames * 259 words. */
+    LPS_FLAG_ACCUM_NORM = 16, /* also accumulate the per-bin sum and sum of squares of the produced frames on the device: the input of
+                                 lps_norm_finalize (qnnorm, tools_pfile/get_norm.pl:4) */
     LPS_FLAG_EXACT = 4        /* execute the reference's split-radix butterfly network itself (bit-identical spectrum, HTK-identical
                                  files) instead of the default register-resident radix-8 FFT (fp32; agrees with the reference to
                                  ~1e-6 of the feature range, see tests/test_lps_gpu.py) */
@@ -54,6 +60,13 @@ int lps_extract(lps_handle *h, const int16_t *pcm, long n_samples, float *out, i
 int lps_extract_batch(lps_handle *h, const int16_t *pcm, const long *utt_off, int n_utts, float *out, int flags, long *total_frames);
 /* device-resident variant; utt_off stays a host array. d_out must hold sum_u lps_nframes(len_u) * 257 floats */
 int lps_extract_batch_device(lps_handle *h, const int16_t *d_pcm, const long *utt_off, int n_utts, float *d_out, int flags, long *total_frames);
+/* .norm production (qnnorm): mean and RECIPROCAL standard deviation (ddof 0) per bin over every frame produced with
+ * LPS_FLAG_ACCUM_NORM since the last lps_norm_reset.  mean / dvar: 257 floats each (host). */
+int lps_norm_reset(lps_handle *h);
+/* the same accumulation for features already on the device: n_frames rows of `pitch` 32-bit words, the 257 values `skip`
+ * words into a row, big-endian when big_endian != 0 (pitch 259 / skip 2 / big_endian 1 = pfile records as they lie in the file) */
+int lps_norm_accumulate_device(lps_handle *h, const float *d_feats, long n_frames, int pitch, int skip, int big_endian);
+int lps_norm_finalize(lps_handle *h, float *mean, float *dvar, long *n_frames);
 /* CUDA-event time (ms) of the kernel(s) of the last call */
 double lps_last_kernel_ms(lps_handle *h);
 const char *lps_last_error(void);

@@ -7,4 +7,5 @@ CPU fallback -- every entry point raises when the library or an sm_100 GPU is mi
 """
 from .bp_gpu import BP_GPU, GGDError, load_library, library_path, FLAG_UNFUSED_UPDATE, FLAG_NO_GRAPH, \
     FLAG_KEEP_DEBUG, FLAG_PIN_HOST, PREC_BF16X3, PREC_FP32_SIMT  # noqa: F401
-from .wav2lps import Wav2LPS, LPSError, lps_nframes, FLAG_BIG_ENDIAN, FLAG_ZSCORE, FLAG_EXACT  # noqa: F401
+from .wav2lps import Wav2LPS, LPSError, lps_nframes, FLAG_BIG_ENDIAN, FLAG_ZSCORE, FLAG_EXACT, \
+    FLAG_PFILE, FLAG_ACCUM_NORM  # noqa: F401

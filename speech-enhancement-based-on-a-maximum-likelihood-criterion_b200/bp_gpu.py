@@ -91,7 +91,7 @@ class RawChunk(C.Structure):
     """ggd_raw_chunk (include/ggd_train.h)"""
     _fields_ = [("fea_records", C.POINTER(C.c_uint)), ("targ_records", C.POINTER(C.c_uint)), ("n_frames", C.c_int), ("n_samples", C.c_int),
                 ("sample_first_frame", C.POINTER(C.c_int)), ("fea_dim", C.c_int), ("fea_context", C.c_int), ("targ_offset", C.c_int),
-                ("mean", C.POINTER(C.c_float)), ("dvar", C.POINTER(C.c_float))]
+                ("mean", C.POINTER(C.c_float)), ("dvar", C.POINTER(C.c_float)), ("rec_frame0", C.c_int), ("rec_frames", C.c_int)]
 
 
 class BP_GPU:

@@ -1024,7 +1024,17 @@ int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *c)
         }
     GGD_CUDA(cudaSetDevice(h->cfg.gpu));
     GGD_TRY(ensure_chunk(h, c->n_samples));
-    const size_t nf = (size_t)c->n_frames * (2 + c->fea_dim), nt = (size_t)c->n_frames * (2 + D);
+    const int world = h->has_comm ? h->cfg.world_size : 1;
+    const bool sliced = c->rec_frames > 0 || c->rec_frame0 > 0;
+    const int S = ceil_div(c->n_frames, world);                 // frames per rank slice
+    if (sliced) {
+        const int want0 = h->cfg.rank * S, wantn = std::max(0, std::min(S, c->n_frames - want0));
+        if (world < 2 || c->rec_frame0 != want0 || c->rec_frames != wantn) {
+            set_error("ggd_train_raw: record slice [%d, +%d) given, rank %d of %d must supply [%d, +%d)", c->rec_frame0, c->rec_frames, h->cfg.rank, world, want0, wantn);
+            return GGD_EINVAL;
+        }
+    }
+    const size_t nf = (size_t)(sliced ? S * world : c->n_frames) * (2 + c->fea_dim), nt = (size_t)(sliced ? S * world : c->n_frames) * (2 + D);
     GGD_TRY(grow(&h->r_fea, &h->r_cap_fea, nf));
     GGD_TRY(grow(&h->r_targ, &h->r_cap_targ, nt));
     GGD_TRY(grow(&h->r_first, &h->r_cap_first, (size_t)c->n_samples));
@@ -1032,8 +1042,19 @@ int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *c)
     // (the record buffers are NOT pinned: their size varies from chunk to chunk, so a caller is free to reallocate them,
     // and a registration that outlives its allocation corrupts the address space; the raw copy is 4x smaller anyway)
     GGD_CUDA(cudaEventRecord(h->ev_c0, h->s_main));
-    GGD_CUDA(cudaMemcpyAsync(h->r_fea, c->fea_records, nf * 4, cudaMemcpyHostToDevice, h->s_main));
-    GGD_CUDA(cudaMemcpyAsync(h->r_targ, c->targ_records, nt * 4, cudaMemcpyHostToDevice, h->s_main));
+    if (sliced) {
+        // my slice lands at its place in the chunk-sized buffers; the other slices arrive over NVLink (in-place all-gather)
+        const size_t wf = (size_t)S * (2 + c->fea_dim), wt = (size_t)S * (2 + D);
+        if (c->rec_frames > 0) {
+            GGD_CUDA(cudaMemcpyAsync(h->r_fea + h->cfg.rank * wf, c->fea_records, (size_t)c->rec_frames * (2 + c->fea_dim) * 4, cudaMemcpyHostToDevice, h->s_main));
+            GGD_CUDA(cudaMemcpyAsync(h->r_targ + h->cfg.rank * wt, c->targ_records, (size_t)c->rec_frames * (2 + D) * 4, cudaMemcpyHostToDevice, h->s_main));
+        }
+        GGD_NCCL(ncclAllGather(h->r_fea + h->cfg.rank * wf, h->r_fea, wf, ncclUint32, h->comm, h->s_main));
+        GGD_NCCL(ncclAllGather(h->r_targ + h->cfg.rank * wt, h->r_targ, wt, ncclUint32, h->comm, h->s_main));
+    } else {
+        GGD_CUDA(cudaMemcpyAsync(h->r_fea, c->fea_records, nf * 4, cudaMemcpyHostToDevice, h->s_main));
+        GGD_CUDA(cudaMemcpyAsync(h->r_targ, c->targ_records, nt * 4, cudaMemcpyHostToDevice, h->s_main));
+    }
     GGD_CUDA(cudaMemcpyAsync(h->r_first, c->sample_first_frame, (size_t)c->n_samples * sizeof(int), cudaMemcpyHostToDevice, h->s_main));
     GGD_CUDA(cudaMemcpyAsync(h->r_norm, c->mean, (size_t)c->fea_dim * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
     GGD_CUDA(cudaMemcpyAsync(h->r_norm + c->fea_dim, c->dvar, (size_t)c->fea_dim * sizeof(float), cudaMemcpyHostToDevice, h->s_main));
@@ -1051,9 +1072,25 @@ int ggd_train_raw(ggd_handle *h, const ggd_raw_chunk *c)
     h->stats.launches += 1;
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev_c0, h->ev_c1);
-    h->stats.h2d_ms = ms; h->stats.h2d_bytes = (nf + nt) * 4 + (size_t)c->n_samples * sizeof(int);
+    h->stats.h2d_ms = ms;
+    h->stats.h2d_bytes = (sliced ? (size_t)c->rec_frames * (4 + c->fea_dim + D) : nf + nt) * 4 + (size_t)c->n_samples * sizeof(int);
     return GGD_OK;
 }
+
+int ggd_bind_thread(ggd_handle *h)
+{
+    if (!h) { set_error("ggd_bind_thread: null handle"); return GGD_EINVAL; }
+    GGD_CUDA(cudaSetDevice(h->cfg.gpu));
+    return GGD_OK;
+}
+
+void *ggd_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); set_error("ggd_host_alloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void ggd_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int ggd_train_device(ggd_handle *h, int n_frames, const float *d_in, const float *d_targ)
 {

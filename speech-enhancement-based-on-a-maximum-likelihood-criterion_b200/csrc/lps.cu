@@ -198,7 +198,12 @@ __global__ void __launch_bounds__(WARPS * 32) lps_kernel(const LpsArgs a)
             __syncwarp();
         }
         // power spectrum + floored natural log (Wav2LogSpec_be.c:469-479); output order Re(0..256), Im(255..1)
-        float *dst = a.out + f * LPS_BINS;
+        const bool pfile = (a.flags & LPS_FLAG_PFILE) != 0;
+        float *dst = a.out + f * (pfile ? LPS_BINS + 2 : LPS_BINS) + (pfile ? 2 : 0);
+        if (pfile && lane == 0) {     // pfile record = {sentence, frame in sentence, 257 floats}, big-endian words (Interface.cc:735-766)
+            dst[-2] = __uint_as_float(__byte_perm((unsigned)lo, 0, 0x0123));
+            dst[-1] = __uint_as_float(__byte_perm((unsigned)(f - a.utt_frame_off[lo]), 0, 0x0123));
+        }
         for (int k = lane; k <= N / 2; k += 32) {
             const float re = x[k];
             float p = __fmul_rn(re, re);
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(WARPS * 32) lps_kernel(const LpsArgs a)
             }
             float v = (p < S.floor_fb) ? -50.0f : __double2float_rn(log((double)p));
             if (a.flags & LPS_FLAG_ZSCORE) v = __fmul_rn(__fsub_rn(v, a.mean[k]), a.dvar[k]);   // Interface.cc:763-764
-            if (a.flags & LPS_FLAG_BIG_ENDIAN) v = __uint_as_float(__byte_perm(__float_as_uint(v), 0, 0x0123));
+            if (a.flags & (LPS_FLAG_BIG_ENDIAN | LPS_FLAG_PFILE)) v = __uint_as_float(__byte_perm(__float_as_uint(v), 0, 0x0123));
             dst[k] = v;
         }
         __syncwarp();
@@ -270,7 +275,7 @@ struct FastArgs {
 };
 
 constexpr int FWARPS = 8;
-__global__ void __launch_bounds__(FWARPS * 32, 2) lps_fast_kernel(const FastArgs a)
+__global__ void __launch_bounds__(FWARPS * 32, 3) lps_fast_kernel(const FastArgs a)
 {
     __shared__ float2 xch[FWARPS][8 * XSTR];          // transpose 1: [k1][b]; transpose 2: Z[k] at k + 4 (k >> 6)
     __shared__ float2 s_post[LPS_BINS];
@@ -340,7 +345,12 @@ __global__ void __launch_bounds__(FWARPS * 32, 2) lps_fast_kernel(const FastArgs
         __syncwarp();
         // split: X[k] = (Zk + conj Zm)/2 + e^{-2 pi i k/512} (Zk - conj Zm)/(2i), m = 256 - k; P = |X|^2; floored ln
         // (Wav2LogSpec_be.c:469-479)
-        float *dst = a.out + f * LPS_BINS;
+        const bool pfile = (a.flags & LPS_FLAG_PFILE) != 0;
+        float *dst = a.out + f * (pfile ? LPS_BINS + 2 : LPS_BINS) + (pfile ? 2 : 0);
+        if (pfile && lane == 0) {     // pfile record = {sentence, frame in sentence, 257 floats}, big-endian words (Interface.cc:735-766)
+            dst[-2] = __uint_as_float(__byte_perm((unsigned)lo, 0, 0x0123));
+            dst[-1] = __uint_as_float(__byte_perm((unsigned)(f - a.utt_frame_off[lo]), 0, 0x0123));
+        }
 #pragma unroll
         for (int j = 0; j < 9; j++) {
             const int k = lane + 32 * j;
@@ -356,12 +366,30 @@ __global__ void __launch_bounds__(FWARPS * 32, 2) lps_fast_kernel(const FastArgs
                 const float pw = 0.25f * fmaf(xr, xr, xi * xi);
                 float val = (pw < floor_fb) ? -50.0f : __logf(pw);
                 if (a.flags & LPS_FLAG_ZSCORE) val = __fmul_rn(__fsub_rn(val, a.mean[k]), a.dvar[k]);   // Interface.cc:763-764
-                if (a.flags & LPS_FLAG_BIG_ENDIAN) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
+                if (a.flags & (LPS_FLAG_BIG_ENDIAN | LPS_FLAG_PFILE)) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
                 dst[k] = val;
             }
         }
         __syncwarp();
     }
+}
+
+// Per-bin sum and sum of squares over frames [f0, f1) in double (qnnorm: mean and reciprocal standard deviation, ddof 0;
+// tools_pfile/get_norm.pl:4).  Rows are `pitch` words apart, the 257 values start `skip` words into a row and are big-endian
+// when `swap` (pfile records).  One thread per bin, frames strided over the grid, one double atomic per thread at the end.
+__global__ void __launch_bounds__(288) lps_norm_kernel(const float *feats, long long f0, long long f1, int pitch, int skip, int swap, double *acc)
+{
+    const int k = threadIdx.x;
+    if (k >= LPS_BINS) return;
+    double s = 0.0, ss = 0.0;
+    for (long long f = f0 + blockIdx.x; f < f1; f += gridDim.x) {
+        unsigned int w = __float_as_uint(feats[f * pitch + skip + k]);
+        if (swap) w = __byte_perm(w, 0, 0x0123);
+        const double v = (double)__uint_as_float(w);
+        s += v; ss += v * v;
+    }
+    atomicAdd(acc + k, s);
+    atomicAdd(acc + LPS_BINS + k, ss);
 }
 
 void build_fast_tab(FastTab &T)
@@ -385,6 +413,7 @@ struct lps_handle {
     int gpu, sm_count;
     Schedule *d_sched;
     FastTab *d_tab;
+    double *d_norm_acc; long long norm_frames;   // running per-bin sum / sum of squares (LPS_FLAG_ACCUM_NORM)
     float *d_mean, *d_dvar;
     bool has_norm;
     cudaStream_t s, s2;                 // s2: second lane of the host-batch pipeline
@@ -430,6 +459,8 @@ int lps_create(int gpu, lps_handle **out)
     LPS_CUDA(cudaMalloc(&h->d_tab, sizeof(FastTab)));
     LPS_CUDA(cudaMemcpy(h->d_tab, T, sizeof(FastTab), cudaMemcpyHostToDevice));
     delete T;
+    LPS_CUDA(cudaMalloc(&h->d_norm_acc, 2 * LPS_BINS * sizeof(double)));
+    LPS_CUDA(cudaMemset(h->d_norm_acc, 0, 2 * LPS_BINS * sizeof(double)));
     LPS_CUDA(cudaMalloc(&h->d_mean, LPS_BINS * sizeof(float)));
     LPS_CUDA(cudaMalloc(&h->d_dvar, LPS_BINS * sizeof(float)));
     LPS_CUDA(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
@@ -446,7 +477,7 @@ int lps_destroy(lps_handle *h)
     cudaSetDevice(h->gpu);
     for (cudaEvent_t e : h->pe) cudaEventDestroy(e);
     if (h->s2) cudaStreamDestroy(h->s2);
-    cudaFree(h->d_tab);
+    cudaFree(h->d_tab); cudaFree(h->d_norm_acc);
     cudaFree(h->d_sched); cudaFree(h->d_mean); cudaFree(h->d_dvar); cudaFree(h->d_pcm); cudaFree(h->d_out); cudaFree(h->d_off);
     cudaEventDestroy(h->e0); cudaEventDestroy(h->e1); cudaStreamDestroy(h->s);
     delete h;
@@ -488,7 +519,7 @@ static int offsets(lps_handle *h, const long *utt_off, int n_utts, std::vector<l
 static int check_flags(lps_handle *h, int flags)
 {
     if ((flags & LPS_FLAG_ZSCORE) && !h->has_norm) { lps_err("LPS_FLAG_ZSCORE needs lps_set_norm first"); return -1; }
-    if ((flags & LPS_FLAG_ZSCORE) && (flags & LPS_FLAG_BIG_ENDIAN)) { lps_err("ZSCORE and BIG_ENDIAN cannot be combined"); return -1; }
+    if ((flags & LPS_FLAG_ZSCORE) && (flags & (LPS_FLAG_BIG_ENDIAN | LPS_FLAG_PFILE))) { lps_err("ZSCORE cannot be combined with BIG_ENDIAN / PFILE"); return -1; }
     return 0;
 }
 
@@ -510,9 +541,16 @@ static int launch_frames(lps_handle *h, const int16_t *d_pcm, int n_utts, long l
         a.pcm = d_pcm; a.utt_sample_off = h->d_off; a.utt_frame_off = h->d_off + n_utts + 1; a.n_utts = n_utts;
         a.frame_begin = f0; a.total_frames = f1; a.out = d_out; a.mean = h->d_mean; a.dvar = h->d_dvar; a.flags = flags; a.tab = h->d_tab;
         long long blocks = (n + FWARPS - 1) / FWARPS;
-        const long long cap = (long long)h->sm_count * 8;   // 2 resident CTAs per SM, 4 rounds for balance
+        const long long cap = (long long)h->sm_count * 12;  // 3 resident CTAs per SM (80 registers), 4 rounds for balance
         if (blocks > cap) blocks = cap;
         lps_fast_kernel<<<(int)blocks, FWARPS * 32, 0, st>>>(a);
+    }
+    if (flags & LPS_FLAG_ACCUM_NORM) {
+        const bool pf = (flags & LPS_FLAG_PFILE) != 0;
+        const int swap = (flags & (LPS_FLAG_BIG_ENDIAN | LPS_FLAG_PFILE)) ? 1 : 0;
+        long long blocks = n < h->sm_count * 8 ? n : h->sm_count * 8;
+        lps_norm_kernel<<<(int)blocks, 288, 0, st>>>(d_out, f0, f1, pf ? LPS_BINS + 2 : LPS_BINS, pf ? 2 : 0, swap, h->d_norm_acc);
+        h->norm_frames += n;
     }
     LPS_CUDA(cudaGetLastError());
     return 0;
@@ -562,7 +600,8 @@ int lps_extract_batch(lps_handle *h, const int16_t *pcm, const long *utt_off, in
         LPS_CUDA(cudaMemcpyAsync(h->d_off, tab.data(), tab.size() * sizeof(long long), cudaMemcpyHostToDevice, h->s));
     }
     if (ns + 16 > h->pcm_cap) { cudaFree(h->d_pcm); h->d_pcm = nullptr; LPS_CUDA(cudaMalloc(&h->d_pcm, (ns + 16) * sizeof(int16_t))); h->pcm_cap = ns + 16; }
-    const size_t no = (size_t)total * LPS_BINS;
+    const size_t pitch = (flags & LPS_FLAG_PFILE) ? LPS_BINS + 2 : LPS_BINS;
+    const size_t no = (size_t)total * pitch;
     if (no > h->out_cap) { cudaFree(h->d_out); h->d_out = nullptr; LPS_CUDA(cudaMalloc(&h->d_out, (no + 1) * sizeof(float))); h->out_cap = no + 1; }
     rc = check_flags(h, flags);
     if (rc) return rc;
@@ -587,7 +626,7 @@ int lps_extract_batch(lps_handle *h, const int16_t *pcm, const long *utt_off, in
         rc = launch_frames(h, h->d_pcm, n_utts, f0, f1, h->d_out, flags, st);
         if (rc) return rc;
         LPS_CUDA(cudaEventRecord(h->pe[2 * p + 1], st));
-        LPS_CUDA(cudaMemcpyAsync(out + f0 * LPS_BINS, h->d_out + f0 * LPS_BINS, (size_t)(f1 - f0) * LPS_BINS * sizeof(float), cudaMemcpyDeviceToHost, st));
+        LPS_CUDA(cudaMemcpyAsync(out + f0 * pitch, h->d_out + f0 * pitch, (size_t)(f1 - f0) * pitch * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     LPS_CUDA(cudaStreamSynchronize(h->s));
     LPS_CUDA(cudaStreamSynchronize(h->s2));
@@ -605,5 +644,46 @@ int lps_extract(lps_handle *h, const int16_t *pcm, long n_samples, float *out, i
 }
 
 double lps_last_kernel_ms(lps_handle *h) { return h ? h->last_ms : 0.0; }
+
+int lps_norm_reset(lps_handle *h)
+{
+    if (!h) { lps_err("lps_norm_reset: null handle"); return -1; }
+    LPS_CUDA(cudaSetDevice(h->gpu));
+    LPS_CUDA(cudaMemset(h->d_norm_acc, 0, 2 * LPS_BINS * sizeof(double)));
+    h->norm_frames = 0;
+    return 0;
+}
+
+int lps_norm_accumulate_device(lps_handle *h, const float *d_feats, long n_frames, int pitch, int skip, int big_endian)
+{
+    if (!h || !d_feats || n_frames < 0 || pitch < LPS_BINS || skip < 0 || skip + LPS_BINS > pitch) { lps_err("lps_norm_accumulate_device: bad argument"); return -1; }
+    if (n_frames == 0) return 0;
+    LPS_CUDA(cudaSetDevice(h->gpu));
+    long long blocks = n_frames < h->sm_count * 8 ? n_frames : h->sm_count * 8;
+    lps_norm_kernel<<<(int)blocks, 288, 0, h->s>>>(d_feats, 0, n_frames, pitch, skip, big_endian ? 1 : 0, h->d_norm_acc);
+    LPS_CUDA(cudaGetLastError());
+    LPS_CUDA(cudaStreamSynchronize(h->s));
+    h->norm_frames += n_frames;
+    return 0;
+}
+
+int lps_norm_finalize(lps_handle *h, float *mean, float *dvar, long *n_frames)
+{
+    if (!h || !mean || !dvar) { lps_err("lps_norm_finalize: null argument"); return -1; }
+    LPS_CUDA(cudaSetDevice(h->gpu));
+    LPS_CUDA(cudaStreamSynchronize(h->s));
+    LPS_CUDA(cudaStreamSynchronize(h->s2));
+    double acc[2 * LPS_BINS];
+    LPS_CUDA(cudaMemcpy(acc, h->d_norm_acc, sizeof acc, cudaMemcpyDeviceToHost));
+    if (n_frames) *n_frames = (long)h->norm_frames;
+    if (h->norm_frames <= 0) { lps_err("lps_norm_finalize: no frames accumulated (LPS_FLAG_ACCUM_NORM)"); return -1; }
+    const double n = (double)h->norm_frames;
+    for (int k = 0; k < LPS_BINS; k++) {
+        const double m = acc[k] / n, var = acc[LPS_BINS + k] / n - m * m;       // ddof 0, like qnnorm
+        mean[k] = (float)m;
+        dvar[k] = (float)(1.0 / sqrt(var > 0 ? var : 1e-300));                   // the .norm file holds the RECIPROCAL std (Interface.cc:385-396)
+    }
+    return 0;
+}
 
 }  // extern "C"

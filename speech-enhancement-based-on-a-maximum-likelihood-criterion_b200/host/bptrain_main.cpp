@@ -102,9 +102,12 @@ int main(int argc, char **argv)
     // byte swap, z-score, context expansion and target selection run on the GPU (ggd_train_raw).  host_loader=1 restores
     // the reference's division of labour (everything on the CPU, ggd_train).
     const bool raw = !p.host_loader;
-    std::vector<unsigned> rfea[2], rtg[2];
+    // page-locked record buffers (ggd_host_alloc): the pread()s land where the DMA engine reads; with several GPUs each rank
+    // reads only its slice of a chunk's records and the library all-gathers the slices over NVLink
+    unsigned *rfea[2] = {nullptr, nullptr}, *rtg[2] = {nullptr, nullptr};
+    size_t rfea_cap[2] = {0, 0}, rtg_cap[2] = {0, 0};
     std::vector<int> first[2];
-    int need[2] = {0, 0};
+    int need[2] = {0, 0}, rec0[2] = {0, 0}, nrec[2] = {0, 0};
     if (!raw) for (int k = 0; k < 2; k++) { in[k].reserve((size_t)p.traincache * p.layersizes[0]); tg[k].reserve((size_t)p.traincache * p.layersizes[p.numlayers - 1]); }
     int samples[2] = {0, 0}, local_samples[2] = {0, 0};
     std::mutex mu;
@@ -112,12 +115,14 @@ int main(int argc, char **argv)
     int filled = 0, consumed = 0;   // chunks produced / released
     bool load_failed = false;
     std::thread loader([&] {
+        ggd_bind_thread(net);     // page-locked allocations of this thread belong to this rank's GPU
         for (int i = 0; i < H.total_chunks; i++) {
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return i - consumed < 2; });
             }
-            const int n = raw ? H.read_chunk_raw(order[i], rfea[i & 1], rtg[i & 1], first[i & 1], &need[i & 1])
+            const int n = raw ? H.read_chunk_raw_slice(order[i], rank, world, &rfea[i & 1], &rfea_cap[i & 1], &rtg[i & 1], &rtg_cap[i & 1], ggd_host_alloc, ggd_host_free,
+                                                       first[i & 1], &need[i & 1], &rec0[i & 1], &nrec[i & 1])
                               : H.read_chunk(order[i], false, in[i & 1], tg[i & 1]);
             int nl = n;
             if (world > 1 && n > 0) {
@@ -148,7 +153,9 @@ int main(int argc, char **argv)
         if (samples[i & 1] % p.bunchsize) printf("this bunch has only %d samples and is ignored.\n", samples[i & 1] % p.bunchsize);
         if (raw) {
             ggd_raw_chunk c;
-            c.fea_records = rfea[i & 1].data(); c.targ_records = rtg[i & 1].data();
+            memset(&c, 0, sizeof c);
+            c.fea_records = rfea[i & 1]; c.targ_records = rtg[i & 1];
+            if (world > 1) { c.rec_frame0 = rec0[i & 1]; c.rec_frames = nrec[i & 1]; }
             c.n_frames = need[i & 1]; c.n_samples = local_samples[i & 1]; c.sample_first_frame = first[i & 1].data();
             c.fea_dim = p.fea_dim; c.fea_context = p.fea_context; c.targ_offset = p.targ_offset;
             c.mean = H.mean_ptr(); c.dvar = H.dvar_ptr();
@@ -160,6 +167,7 @@ int main(int argc, char **argv)
     }
     { std::lock_guard<std::mutex> lk(mu); consumed = H.total_chunks + 2; cv.notify_all(); }
     loader.join();
+    for (int k = 0; k < 2; k++) { ggd_host_free(rfea[k]); ggd_host_free(rtg[k]); }
     if (rc) return rc;
     H.logf("Total cost time: %.1f s.\n", (double)(time(nullptr) - t0));
     if (rank > 0) {

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <thread>
 #include <unistd.h>
@@ -338,8 +339,11 @@ int Host::read_chunk(int idx, bool cv, std::vector<float> &in, std::vector<float
     return samples;
 }
 
-// Readchunk (Interface.cc:719-838) without its arithmetic: raw records + row -> first-frame map (see interface.h)
-int Host::read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<unsigned> &targ_rec, std::vector<int> &first, int *need_out)
+// Readchunk (Interface.cc:719-838) without its arithmetic: raw records + row -> first-frame map (see interface.h).
+// The records of frames [rec0, rec0 + nrec) of the chunk are read into caller-owned buffers (page-locked in the trainer);
+// the row map depends only on the sentence table, so every data-parallel rank builds the same map from its own slice.
+int Host::read_chunk_raw_slice(int idx, int rank, int world, unsigned **fea_buf, size_t *fea_cap, unsigned **targ_buf, size_t *targ_cap,
+                               void *(*alloc)(size_t), void (*release)(void *), std::vector<int> &first, int *need_out, int *rec0_out, int *nrec_out)
 {
     const int D = p.layersizes[p.numlayers - 1], fd = p.fea_dim, ctx = p.fea_context;
     int need, samples;
@@ -349,23 +353,36 @@ int Host::read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<un
     for (int i = 0; i < samples; i++) order[i] = i;
     shuffle(order);                                                        // per-sample shuffle, :750-754
     first.assign(samples, 0);
+    const int S = (need + world - 1) / world;
+    const int rec0 = world > 1 ? rank * S : 0;
+    const int nrec = world > 1 ? std::max(0, std::min(S, need - rec0)) : need;
     // both streams at once, each with read_threads concurrent pread()s (the records of a chunk are contiguous in the pfile)
     bool ok_stream[2] = {true, true};
     std::thread readers[2];
     for (int stream = 0; stream < 2; stream++) {
         const int dim = stream == 0 ? fd : D;
         FILE *fp = stream == 0 ? fp_data : fp_targ;
-        std::vector<unsigned> &raw = stream == 0 ? fea_rec : targ_rec;
+        unsigned **buf = stream == 0 ? fea_buf : targ_buf;
+        size_t *cap = stream == 0 ? fea_cap : targ_cap;
         const long rec = 4L * (dim + 2);
-        raw.resize((size_t)need * (dim + 2));
-        readers[stream] = std::thread([=, &raw, &ok_stream] {
-            ok_stream[stream] = pread_parallel(fileno(fp), raw.data(), (size_t)need * rec, (off_t)kPfileHeader + (off_t)chunk_st[idx] * rec, p.read_threads);
+        const size_t bytes = (size_t)std::max(nrec, 1) * rec;
+        if (bytes > *cap) {
+            if (*buf) release(*buf);
+            *cap = bytes + bytes / 8;
+            *buf = (unsigned *)alloc(*cap);
+            if (!*buf) { *cap = 0; logf("cannot allocate %zu bytes for the records of chunk %d.\n", bytes, idx); return -1; }
+        }
+        unsigned *dst = *buf;
+        readers[stream] = std::thread([=, &ok_stream] {
+            ok_stream[stream] = nrec == 0 || pread_parallel(fileno(fp), dst, (size_t)nrec * rec, (off_t)kPfileHeader + (off_t)(chunk_st[idx] + rec0) * rec, p.read_threads);
         });
     }
     for (auto &r : readers) r.join();
     for (int stream = 0; stream < 2; stream++)
         if (!ok_stream[stream]) { logf("%s pfile short read in chunk %d.\n", stream ? "targ" : "data", idx); return -1; }
-    int cur_sent = (int)bswap32(fea_rec[0]);
+    // sentence that contains the first frame of the chunk (the reference reads it from the first record, Interface.cc:744)
+    int cur_sent = (int)(std::upper_bound(frames_before_sent.begin(), frames_before_sent.end(), chunk_st[idx]) - frames_before_sent.begin());
+    if (rec0 == 0 && nrec > 0 && (int)bswap32((*fea_buf)[0]) != cur_sent) { logf("chunk %d: sentence id %d of the first record disagrees with the sentence table (%d).\n", idx, (int)bswap32((*fea_buf)[0]), cur_sent); return -1; }
     int processed = 0, cur_frame = chunk_st[idx], cur_sample = 0;
     while (processed != need) {
         int n;
@@ -381,7 +398,22 @@ int Host::read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<un
         processed += n;
     }
     *need_out = need;
+    if (rec0_out) *rec0_out = rec0;
+    if (nrec_out) *nrec_out = nrec;
     return samples;
+}
+
+int Host::read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<unsigned> &targ_rec, std::vector<int> &first, int *need_out)
+{
+    unsigned *fb = nullptr, *tb = nullptr;
+    size_t fc = 0, tc = 0;
+    const int n = read_chunk_raw_slice(idx, 0, 1, &fb, &fc, &tb, &tc, malloc, free, first, need_out, nullptr, nullptr);
+    if (n >= 0) {
+        fea_rec.assign(fb, fb + (size_t)*need_out * (2 + p.fea_dim));
+        targ_rec.assign(tb, tb + (size_t)*need_out * (2 + p.layersizes[p.numlayers - 1]));
+    }
+    free(fb); free(tb);
+    return n;
 }
 
 bool Host::write_weights()

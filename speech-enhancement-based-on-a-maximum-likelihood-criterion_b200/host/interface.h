@@ -41,6 +41,10 @@ public:
     // the same chunk for the device-side loader (ggd_train_raw): the raw big-endian records as they lie in the pfiles and,
     // per shuffled net-input row, its first context frame inside the chunk; consumes the same random numbers as read_chunk
     int read_chunk_raw(int idx, std::vector<unsigned> &fea_rec, std::vector<unsigned> &targ_rec, std::vector<int> &first, int *need_out);
+    // the same with caller-owned (e.g. page-locked) record buffers, grown through alloc / release; with world > 1 only the
+    // records of this rank's slice [rank*S, rank*S + S) of the chunk, S = ceil(need / world), are read (ggd_raw_chunk::rec_frame0)
+    int read_chunk_raw_slice(int idx, int rank, int world, unsigned **fea_buf, size_t *fea_cap, unsigned **targ_buf, size_t *targ_cap,
+                             void *(*alloc)(size_t), void (*release)(void *), std::vector<int> &first, int *need_out, int *rec0_out, int *nrec_out);
     const float *mean_ptr() const { return mean.data(); }
     const float *dvar_ptr() const { return dvar.data(); }
     bool write_weights();                                     // Interface::Writeweights, Interface.cc:484-516

@@ -3,7 +3,7 @@ import ctypes as C
 import numpy as np
 from .bp_gpu import load_library
 
-FLAG_BIG_ENDIAN, FLAG_ZSCORE, FLAG_EXACT = 1, 2, 4
+FLAG_BIG_ENDIAN, FLAG_ZSCORE, FLAG_EXACT, FLAG_PFILE, FLAG_ACCUM_NORM = 1, 2, 4, 8, 16
 PF = C.POINTER(C.c_float)
 PS = C.POINTER(C.c_int16)
 PL = C.POINTER(C.c_long)
@@ -25,6 +25,9 @@ def _lib():
         L.lps_extract.argtypes = [C.c_void_p, PS, C.c_long, PF, C.c_int]
         L.lps_extract_batch.argtypes = [C.c_void_p, PS, PL, C.c_int, PF, C.c_int, PL]
         L.lps_extract_batch_device.argtypes = [C.c_void_p, C.c_void_p, PL, C.c_int, C.c_void_p, C.c_int, PL]
+        L.lps_norm_reset.argtypes = [C.c_void_p]
+        L.lps_norm_finalize.argtypes = [C.c_void_p, PF, PF, PL]
+        L.lps_norm_accumulate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int]
         L.lps_last_kernel_ms.restype = C.c_double
         L.lps_last_kernel_ms.argtypes = [C.c_void_p]
         L._lps_ready = True
@@ -76,7 +79,7 @@ class Wav2LPS:
         pcm = np.ascontiguousarray(pcm, np.int16)
         off = np.ascontiguousarray(utt_off, np.int64)
         total = sum(lps_nframes(int(off[i + 1] - off[i])) for i in range(len(off) - 1))
-        out = np.zeros((total, 257), np.float32)
+        out = np.zeros((total, 259 if flags & FLAG_PFILE else 257), np.float32)   # FLAG_PFILE: raw big-endian record words
         n = C.c_long()
         self._ck(self.L.lps_extract_batch(self.h, pcm.ctypes.data_as(PS), off.ctypes.data_as(PL), len(off) - 1,
                                           out.ctypes.data_as(PF), flags, C.byref(n)))
@@ -89,6 +92,22 @@ class Wav2LPS:
         self._ck(self.L.lps_extract_batch_device(self.h, C.c_void_p(d_pcm_ptr), off.ctypes.data_as(PL), len(off) - 1,
                                                  C.c_void_p(d_out_ptr), flags, C.byref(n)))
         return n.value
+
+    def norm_reset(self):
+        self._ck(self.L.lps_norm_reset(self.h))
+
+    def norm_of_device_features(self, d_feats_ptr, n_frames, pitch=257, skip=0, big_endian=False):
+        """qnnorm over features resident on the device (e.g. the records of an existing pfile: pitch 259, skip 2, big_endian)"""
+        self.norm_reset()
+        self._ck(self.L.lps_norm_accumulate_device(self.h, C.c_void_p(d_feats_ptr), n_frames, pitch, skip, int(big_endian)))
+        mean, dvar, _ = self.norm_finalize()
+        return mean, dvar
+
+    def norm_finalize(self):
+        """(mean, reciprocal std, frames) over everything extracted with FLAG_ACCUM_NORM since norm_reset (qnnorm)"""
+        mean, dvar, n = np.zeros(257, np.float32), np.zeros(257, np.float32), C.c_long()
+        self._ck(self.L.lps_norm_finalize(self.h, mean.ctypes.data_as(PF), dvar.ctypes.data_as(PF), C.byref(n)))
+        return mean, dvar, n.value
 
     def last_kernel_ms(self):
         return float(self.L.lps_last_kernel_ms(self.h))

@@ -21,6 +21,10 @@ def load_pkg():
     name = "se_ml_b200"
     if name in sys.modules:
         return sys.modules[name]
+    try:                      # torch must come first: importing it AFTER libggd_b200.so has pulled in its own CUDA / NCCL libraries fails
+        import torch  # noqa: F401
+    except Exception:
+        pass
     spec = importlib.util.spec_from_file_location(name, os.path.join(PKG_DIR, "__init__.py"),
                                                   submodule_search_locations=[PKG_DIR])
     mod = importlib.util.module_from_spec(spec)

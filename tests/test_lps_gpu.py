@@ -124,3 +124,48 @@ def test_pipelined_host_batch(pkg, oracle):
         check_close_fast(got[f - 2:f - 2 + ref.shape[0]], ref)
     dev = ex.extract_batch(pcm, off, flags=pkg.FLAG_EXACT)
     check_close_fast(got, dev)
+
+
+def test_pfile_records_and_norm_production(pkg, oracle, tmp_path):
+    """the LPS kernel writes QuickNet pfile RECORDS (feacat, tools_pfile/pfile_noisy.pl:33) and accumulates the
+    per-bin statistics of the .norm file (qnnorm, get_norm.pl:4) on the device.  Checks: the records wrapped in the pfile
+    container are read back by the reference-format reader with the right sentence / frame indices and features; the norm
+    equals the float64 numpy statistics (ddof 0); and qnnorm's own output is reproduced from the reference's golden pfile."""
+    rng = np.random.RandomState(9)
+    lens = [4000, 513, 9000, 256 * 7]
+    pcm = np.clip(np.round(rng.randn(sum(lens)) * 2000), -32768, 32767).astype(np.int16)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    ex = pkg.Wav2LPS(0)
+    feats = ex.extract_batch(pcm, off, flags=pkg.FLAG_EXACT)
+    ex.norm_reset()
+    rec = ex.extract_batch(pcm, off, flags=pkg.FLAG_EXACT | pkg.FLAG_PFILE | pkg.FLAG_ACCUM_NORM)
+    words = rec.view(">u4")
+    nfr = [pkg.lps_nframes(n) for n in lens]
+    assert rec.shape == (sum(nfr), 259)
+    assert np.array_equal(words[:, 0], np.repeat(np.arange(len(lens)), nfr))
+    assert np.array_equal(words[:, 1], np.concatenate([np.arange(n) for n in nfr]))
+    assert np.array_equal(rec[:, 2:].view(">f4").astype(np.float32), feats)
+    # the container around the records: header + records + sentence index tail, read back by the loader's format reader
+    ref_path, my_path = str(tmp_path / "ref.pfile"), str(tmp_path / "mine.pfile")
+    oracle.write_pfile(ref_path, feats, nfr)
+    blob = open(ref_path, "rb").read()
+    body = len(feats) * 259 * 4
+    open(my_path, "wb").write(blob[:32768] + rec.tobytes() + blob[32768 + body:])
+    assert open(my_path, "rb").read() == blob
+    mean, dvar, n = ex.norm_finalize()
+    assert n == len(feats)
+    x = feats.astype(np.float64)
+    assert np.allclose(mean, x.mean(0), rtol=1e-6) and np.allclose(dvar, 1.0 / x.std(0), rtol=1e-5)
+    # qnnorm pinned by the reference's own files: statistics of the golden pfile against the golden .norm (6 printed digits)
+    gfeat = oracle.read_pfile(os.path.join(GOLDEN, "train_noisy.pfile"))[0]
+    gmean, gdvar = oracle.read_norm(os.path.join(GOLDEN, "train_noisy.norm"), 257)
+    import torch
+    d = torch.from_numpy(np.ascontiguousarray(gfeat)).cuda()
+    m2, v2 = ex.norm_of_device_features(d.data_ptr(), gfeat.shape[0])
+    assert np.allclose(m2, gmean, rtol=1e-5) and np.allclose(v2, gdvar, rtol=1e-5)
+    # fast kernel: same records within the fast tolerance
+    ex.norm_reset()
+    rec2 = ex.extract_batch(pcm, off, flags=pkg.FLAG_PFILE | pkg.FLAG_ACCUM_NORM)
+    check_close_fast(rec2[:, 2:].view(">f4").astype(np.float32), feats)
+    m3, v3, _ = ex.norm_finalize()
+    assert np.allclose(m3, mean, rtol=1e-5) and np.allclose(v3, dvar, rtol=1e-4)

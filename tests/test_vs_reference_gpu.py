@@ -155,3 +155,42 @@ def test_wav2lps_cli(pkg, oracle, tmp_path):
     assert ha == hb
     assert np.mean(fa.view(np.uint32) != fb.view(np.uint32)) < 1e-3
     assert np.all(np.abs(fa - fb) <= 1e-4 * np.maximum(np.abs(fb), 1.0))
+
+
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
+def test_cli_multi_gpu_equals_single_gpu(pkg, oracle, tmp_path, ngpu):
+    """the drop-in executable with gpu_used=0,...,N-1 (forked workers, frame-sharded: bunchsize stays the GLOBAL minibatch,
+    every rank reads only its slice of the chunk's pfile records and the library all-gathers them over NVLink) writes the
+    same .wts and CV lines as the one-GPU run with the same finetune.pl flags (tolerance 1e-3)"""
+    import torch
+    if torch.cuda.device_count() < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    O = oracle
+    mine = os.path.join(PKG_DIR, "host", "BPtrain_Sigmoid")
+    if not os.path.exists(mine):
+        pytest.skip("host/BPtrain_Sigmoid not built")
+    ls = [1799, 2048, 2048, 2048, 257]
+    W, b = O.init_weights(ls, seed=4)
+    init = str(tmp_path / "init.wts")
+    O.write_wts(init, ls, W, b)
+
+    def flags(tag, gpus):
+        return ["gpu_used=" + gpus, "numlayers=5", "layersizes=1799,2048,2048,2048,257", "bunchsize=128", "MLflag=1",
+                "shapefactor=1.5", "momentum=0.9", "weightcost=0.00001", "lrate=0.1", "fea_dim=257", "fea_context=7",
+                "traincache=102400", "init_randem_seed=27870775", "targ_offset=3", "initwts_file=" + init,
+                "norm_file=" + os.path.join(GOLDEN, "train_noisy.norm"), "fea_file=" + os.path.join(GOLDEN, "train_noisy.pfile"),
+                "targ_file=" + os.path.join(GOLDEN, "train_clean.pfile"), "outwts_file=" + str(tmp_path / (tag + ".wts")),
+                "log_file=" + str(tmp_path / (tag + ".log")), "train_sent_range=0-7", "cv_sent_range=8-9", "dropoutflag=0",
+                "visible_omit=0.1", "hid_omit=0.1"]
+    subprocess.run([mine] + flags("one", "0"), check=True, cwd=str(tmp_path), stdout=subprocess.DEVNULL, timeout=300)
+    subprocess.run([mine] + flags("many", ",".join(str(i) for i in range(ngpu))), check=True, cwd=str(tmp_path), stdout=subprocess.DEVNULL, timeout=300)
+    v1, vn = _log_values(str(tmp_path / "one.log")), _log_values(str(tmp_path / "many.log"))
+    assert vn["samples"] == v1["samples"] == 1443 and vn["cv_samples"] == v1["cv_samples"] == 382
+    W1, b1 = O.read_wts(str(tmp_path / "one.wts"), ls)
+    Wn, bn = O.read_wts(str(tmp_path / "many.wts"), ls)
+    for l in range(4):
+        assert rel_err(Wn[l], W1[l]) < 1e-3, l
+        assert rel_err(Wn[l] - W[l], W1[l] - W[l]) < 2e-3, "update of layer %d" % (l + 1)
+        assert rel_err(bn[l], b1[l]) < 2e-3, l
+    for k in ("sq", "abs", "ll"):
+        assert abs(vn[k] - v1[k]) <= 2e-3 * abs(v1[k]), k
