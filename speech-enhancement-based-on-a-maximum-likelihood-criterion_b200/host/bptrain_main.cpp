@@ -9,6 +9,7 @@
 // are those of the one-GPU run with the same flags (within the arithmetic tolerance).  Rank 0 alone writes files.
 #include "../../include/ggd_train.h"
 #include "interface.h"
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <ctime>
@@ -32,9 +33,13 @@ static std::vector<int> scan_gpus(int argc, char **argv)
     return g;
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int main(int argc, char **argv)
 {
     const time_t t0 = time(nullptr);
+    const double T0 = now_s();
+    const bool timing = getenv("GGD_CLI_TIMING") != nullptr;     // per-phase wall times on stderr (tuning aid)
     // ---- data parallelism: one process per listed GPU, forked BEFORE anything touches CUDA
     const std::vector<int> gpus = scan_gpus(argc, argv);
     const int world = (int)gpus.size();
@@ -87,8 +92,10 @@ int main(int argc, char **argv)
     const float *Wp[GGD_MAXLAYER] = {nullptr}, *bp[GGD_MAXLAYER] = {nullptr};
     for (int l = 1; l < p.numlayers; l++) { Wp[l] = H.W[l].data(); bp[l] = H.b[l].data(); }
     ggd_handle *net = nullptr;
+    if (timing) fprintf(stderr, "[rank %d] %.3f s: host init done (norm, weights, files)\n", rank, now_s() - T0);
     if (ggd_create(&cfg, Wp, bp, &net) != GGD_OK) { H.logf("%s\n", ggd_last_error()); printf("%s\n", ggd_last_error()); return 1; }
     printf("Created net with %d layers, bunchsize %d.\n", p.numlayers, p.bunchsize);
+    if (timing) fprintf(stderr, "[rank %d] %.3f s: ggd_create done (CUDA context, NCCL, peer mapping)\n", rank, now_s() - T0);
     if (!H.pfile_info()) return 1;
 
     // ---- train
@@ -121,9 +128,11 @@ int main(int argc, char **argv)
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return i - consumed < 2; });
             }
+            const double tl0 = now_s();
             const int n = raw ? H.read_chunk_raw_slice(order[i], rank, world, &rfea[i & 1], &rfea_cap[i & 1], &rtg[i & 1], &rtg_cap[i & 1], ggd_host_alloc, ggd_host_free,
                                                        first[i & 1], &need[i & 1], &rec0[i & 1], &nrec[i & 1])
                               : H.read_chunk(order[i], false, in[i & 1], tg[i & 1]);
+            if (timing) fprintf(stderr, "[rank %d] %.3f s: chunk %d loaded in %.1f ms\n", rank, now_s() - T0, i, (now_s() - tl0) * 1e3);
             int nl = n;
             if (world > 1 && n > 0) {
                 // this rank's rows of every GLOBAL bunch (the trailing partial bunch is dropped by the trainer anyway)
@@ -144,12 +153,14 @@ int main(int argc, char **argv)
     });
     int rc = 0;
     for (int i = 0; i < H.total_chunks && rc == 0; i++) {
+        const double tw0 = now_s();
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return filled > i || load_failed; });
             if (load_failed) { rc = 1; break; }
         }
         H.logf("Starting chunk %d of %d containing %d samples.\n", i + 1, H.total_chunks, samples[i & 1]);
+        const double tt0 = now_s();
         if (samples[i & 1] % p.bunchsize) printf("this bunch has only %d samples and is ignored.\n", samples[i & 1] % p.bunchsize);
         if (raw) {
             ggd_raw_chunk c;
@@ -161,6 +172,7 @@ int main(int argc, char **argv)
             c.mean = H.mean_ptr(); c.dvar = H.dvar_ptr();
             if (ggd_train_raw(net, &c) != GGD_OK) { H.logf("%s\n", ggd_last_error()); rc = 1; }
         } else if (ggd_train(net, samples[i & 1], in[i & 1].data(), tg[i & 1].data()) != GGD_OK) { H.logf("%s\n", ggd_last_error()); rc = 1; }
+        if (timing) fprintf(stderr, "[rank %d] %.3f s: chunk %d trained in %.1f ms (waited for it %.1f ms)\n", rank, now_s() - T0, i, (now_s() - tt0) * 1e3, (tt0 - tw0) * 1e3);
         std::lock_guard<std::mutex> lk(mu);
         consumed = i + 1;
         cv.notify_all();

@@ -141,7 +141,14 @@ def stage_epoch(world, frames, bunch, cache):
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
     T = tempfile.mkdtemp(dir=base)
     t0 = time.time()
-    lens = make_pfiles(T, frames)
+    try:
+        lens = make_pfiles(T, frames)
+    except OSError as ex:            # /dev/shm too small for 2 x 23 GB: fall back to half the frames and say so
+        for f in os.listdir(T):
+            os.remove(os.path.join(T, f))
+        frames //= 2
+        sys.stderr.write("pfile generation failed (%s): retrying with %d frames\n" % (ex, frames))
+        lens = make_pfiles(T, frames)
     gen_s = time.time() - t0
     ls = [1799, 2048, 2048, 2048, 257]
     W, b = O.init_weights(ls, seed=4)
@@ -155,7 +162,7 @@ def stage_epoch(world, frames, bunch, cache):
     train = sum(max(0, n - 6) for n in lens[:len(lens) - ncv])
     exe = os.path.join(PKG, "host", "BPtrain_Sigmoid")
     t0 = time.time()
-    p = subprocess.run([exe] + flags, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=3000)
+    p = subprocess.run([exe] + flags, stdout=subprocess.PIPE, stderr=subprocess.STDOUT if not os.environ.get("GGD_CLI_TIMING") else None, timeout=3000)
     wall = time.time() - t0
     log = open(T + "/train.log").read() if os.path.exists(T + "/train.log") else ""
     cost = [l for l in log.splitlines() if l.startswith("Total cost time")]
