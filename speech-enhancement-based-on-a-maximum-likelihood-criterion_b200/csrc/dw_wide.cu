@@ -16,15 +16,15 @@
 // 64 w k x 32 frames hi+lo); two 256-column fp32 accumulators alternate in TMEM (all 512 columns), so the MMAs of
 // segment t+1 run under the update of segment t.
 //
-// Warp roles (384 threads, one CTA per SM):
+// Warp roles (416 threads, one CTA per SM):
 //   warp 0      operand producer (TMA).  In data-parallel mode it first waits (bounded) for the peers' flags of the layer.
 //   warp 1      TMEM allocator + single-thread tcgen05 MMA issuer (bf16x3: lo*hi + hi*lo + hi*hi, small terms first)
 //   warps 2..9  update warps: gradient quarter (16 k rows x 128 n) from TMEM, W / delta from the ring stage,
 //               delta <- mom*delta - lr*(g/Mg + wc*W), W <- W + delta, written back in place
 //   warp 10     store warp: TMA stores of W and delta, releases the stage once the store engine has read it
 //   warp 11     weight producer: fp32 W and delta quarter tiles by TMA, running ahead of the update by the ring depth
-// All weight traffic is TMA.  HBM bytes: 16 B/param (read W, delta; write W, delta).  The bias gradients + bias update are the
-// kernel's tail: every CTA that has finished its slabs sums its share of the dE/dx columns over the whole minibatch.
+//   warp 12     bias warp: column sums of dE/dx over the whole minibatch + bias update for this CTA's share of the columns
+// All weight traffic is TMA.  HBM bytes: 16 B/param (read W, delta; write W, delta).
 #include "dp_factor.cuh"
 #include "pipe.cuh"
 #include "../../include/ggd_train.h"
@@ -42,7 +42,7 @@ constexpr int WD_ROWS = 16;
 constexpr int WD_F32 = WD_ROWS * TN * 4;           // 8 KB: 16 k x 128 n fp32
 constexpr int WD_STAGE = 2 * WD_F32;               // W + delta
 constexpr int MAX_OPS = 4, MAX_WDS = 8;
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 416;                     // 13 warps: see the role list
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;
 }  // namespace dww
@@ -52,20 +52,25 @@ struct WSeg {
     int li, nt, ks, w;
 };
 
-// Every CTA takes the same share of EVERY layer (a contiguous sub-range of the layer's slabs), walking the layers in list
-// order: in data-parallel mode the factors of the top layers arrive first, so nobody idles waiting for the bottom layer.
+// Slab GROUPS: the layers (in list order, top layer first) are joined into groups; every group's slab list is cut into
+// gridDim.x contiguous ranges and a CTA walks its range of group 0, then of group 1, ...  One GPU: one group (the fewest, widest
+// segments).  Data parallel: the bottom layer is a group of its own -- its dE/dx factors arrive last, ~10-20 us after the
+// backward chain, so every CTA first works through its share of the upper layers and nobody idles waiting for the peers.
 struct SegIter {
     const DwwArgs *gp;
-    int li, s, s1;
-    __device__ __forceinline__ explicit SegIter(const DwwArgs *g) : gp(g), li(-1), s(0), s1(0) {}
+    int grp, s, s1;
+    __device__ __forceinline__ explicit SegIter(const DwwArgs *g) : gp(g), grp(-1), s(0), s1(0) {}
     __device__ __forceinline__ bool next(WSeg &g)
     {
         while (s >= s1) {
-            if (++li >= gp->nlayers) return false;
-            const DwwLayer *L = &gp->layer[li];
-            s = L->slab_base + (int)((long long)L->n_slabs * blockIdx.x / gridDim.x);
-            s1 = L->slab_base + (int)((long long)L->n_slabs * (blockIdx.x + 1) / gridDim.x);
+            if (++grp >= gp->ngroups) return false;
+            const int b = gp->group_base[grp], n = gp->group_base[grp + 1] - b;
+            s = b + (int)((long long)n * blockIdx.x / gridDim.x);
+            s1 = b + (int)((long long)n * (blockIdx.x + 1) / gridDim.x);
         }
+        int li = 0;
+#pragma unroll 1
+        while (li + 1 < gp->nlayers && s >= gp->layer[li + 1].slab_base) li++;
         const DwwLayer *L = &gp->layer[li];
         const int r = s - L->slab_base;
         g.L = L; g.li = li; g.nt = r / L->k_slabs; g.ks = r - g.nt * L->k_slabs;
@@ -237,6 +242,56 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
             tma_store_wait_all<0>();   // all writes performed before the CTA (and with it the grid) completes
         }
         __syncwarp();
+    } else if (warp == 12) {
+        // ===== bias warp (kernAccSumrow + updatedelta + DevAccSum, DevFunc.cu:267-285; BP_GPU.cu:434-437): column sums of dE/dx
+        // over the WHOLE minibatch in a fixed order (identical on every rank) and the bias update, 32 columns per item, items dealt
+        // round-robin to the CTAs.  It runs BESIDE the slab pipeline (latency-bound L2 reads), not as a kernel of its own: a second
+        // kernel spinning on the peers' flags can fill the SMs and starve the very push kernels the peers wait for.
+        const unsigned int step = gp->world > 1 ? *gp->step_counter + 1u : 0u;
+        const int cpair = lane & 15, half = lane >> 4;      // 16 column pairs x 2 row halves (even / odd frames)
+        int item = 0;
+        for (int li = 0; li < gp->nlayers; li++) {
+            const DwwLayer *L = &gp->layer[li];
+            const int nblk = (L->N + 31) / 32;
+            bool waited = false;
+            for (int bk = 0; bk < nblk; bk++, item++) {
+                if (item % (int)gridDim.x != (int)blockIdx.x) continue;
+                if (!waited && gp->world > 1) {
+                    if (lane == 0) wide_wait_flags(gp, L->ev_dx, step);
+                    __syncwarp();
+                    waited = true;
+                }
+                const int n = bk * 32 + 2 * cpair;
+                float s0 = 0.0f, s1 = 0.0f;
+                if (n < L->Np) {
+                    const unsigned int *ph = reinterpret_cast<const unsigned int *>(L->dx_hi + n), *pl = reinterpret_cast<const unsigned int *>(L->dx_lo + n);
+                    const size_t pitch = (size_t)L->Np / 2;            // row pitch in 32-bit words (Np is a multiple of 64)
+                    int m = half;
+                    for (; m + 30 < gp->rows; m += 32) {               // 16 rows of this half per round, loads first
+                        unsigned int vh[16], vl[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) { vh[u] = __ldcg(ph + (size_t)(m + 2 * u) * pitch); vl[u] = __ldcg(pl + (size_t)(m + 2 * u) * pitch); }
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            s0 += __uint_as_float(vh[u] << 16) + __uint_as_float(vl[u] << 16);
+                            s1 += __uint_as_float(vh[u] & 0xFFFF0000u) + __uint_as_float(vl[u] & 0xFFFF0000u);
+                        }
+                    }
+                    for (; m < gp->rows; m += 2) {
+                        const unsigned int vh = __ldcg(ph + (size_t)m * pitch), vl = __ldcg(pl + (size_t)m * pitch);
+                        s0 += __uint_as_float(vh << 16) + __uint_as_float(vl << 16);
+                        s1 += __uint_as_float(vh & 0xFFFF0000u) + __uint_as_float(vl & 0xFFFF0000u);
+                    }
+                }
+                // even-frame half + odd-frame half, fixed order
+                const float o0 = __shfl_xor_sync(0xffffffffu, s0, 16), o1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+                if (half == 0) {
+                    const float g0 = s0 + o0, g1 = s1 + o1;
+                    if (n < L->N) { const float db = gp->mom * L->db[n] - gp->lr * (g0 / gp->Mg); L->db[n] = db; L->b[n] = db + L->b[n]; }      // no weight cost on biases (BP_GPU.cu:435)
+                    if (n + 1 < L->N) { const float db = gp->mom * L->db[n + 1] - gp->lr * (g1 / gp->Mg); L->db[n + 1] = db; L->b[n + 1] = db + L->b[n + 1]; }
+                }
+            }
+        }
     } else if (warp == 11) {
         if (lane == 0) {
             // ===== weight producer: W and delta quarter tiles, ahead of the update by the ring depth =====
@@ -264,7 +319,7 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp >= 2 && warp <= 9) {
         // ===== update warps (8): quadrant q = accumulator lanes [32q, 32q+32); `h` = which 8 of a stage's 16 rows =====
         const int e = warp - 2, q = warp & 3, h = e >> 2;
         const float mom = gp->mom, lr = gp->lr, inv_mg = 1.0f / gp->Mg;
@@ -311,48 +366,6 @@ __global__ void __launch_bounds__(dww::NTHREADS, 1) dw_wide_kernel(const DwwArgs
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem);
-    // ===== biases (kernAccSumrow + updatedelta + DevAccSum, DevFunc.cu:267-285; BP_GPU.cu:434-437): column sums of dE/dx over the
-    // WHOLE minibatch in a fixed order (identical on every rank), 32 columns per item, items dealt round-robin to the CTAs.
-    // Done HERE, by the CTAs that have finished their slabs, rather than by a kernel of its own: a second kernel spinning on the
-    // peers' flags can fill the SMs and starve the very push kernels the peers are waiting for (a real deadlock in eager mode).
-    {
-        float(*red)[33] = reinterpret_cast<float(*)[33]>(smem);     // the pipeline has drained: 12 x 33 floats of the ring
-        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 columns x 12 row lanes
-        const unsigned int step = gp->world > 1 ? *gp->step_counter + 1u : 0u;
-        int item = 0;
-        for (int li = 0; li < gp->nlayers; li++) {
-            const DwwLayer *L = &gp->layer[li];
-            const int nblk = (L->N + 31) / 32;
-            bool mine = false;
-            for (int bk = 0; bk < nblk; bk++) mine |= ((item + bk) % (int)gridDim.x) == (int)blockIdx.x;
-            if (mine && gp->world > 1) {
-                if (threadIdx.x == 0) wide_wait_flags(gp, L->ev_dx, step);     // (long since raised; CTAs without slabs in this layer never looked)
-                __syncthreads();
-            }
-            for (int bk = 0; bk < nblk; bk++, item++) {
-                if (item % (int)gridDim.x != (int)blockIdx.x) continue;
-                const int n = bk * 32 + tx;
-                float sacc = 0.0f;
-                if (n < L->N)
-                    for (int m = ty; m < gp->rows; m += NTHREADS / 32) {
-                        const unsigned short hv = __ldcg(reinterpret_cast<const unsigned short *>(L->dx_hi) + (size_t)m * L->Np + n);
-                        const unsigned short lv = __ldcg(reinterpret_cast<const unsigned short *>(L->dx_lo) + (size_t)m * L->Np + n);
-                        sacc += __uint_as_float((unsigned int)hv << 16) + __uint_as_float((unsigned int)lv << 16);
-                    }
-                red[ty][tx] = sacc;
-                __syncthreads();
-                if (ty == 0 && n < L->N) {
-                    float g = red[0][tx];
-#pragma unroll
-                    for (int r = 1; r < NTHREADS / 32; r++) g += red[r][tx];
-                    const float db = gp->mom * L->db[n] - gp->lr * (g / gp->Mg);   // no weight cost on biases (BP_GPU.cu:435)
-                    L->db[n] = db;
-                    L->b[n] = db + L->b[n];
-                }
-                __syncthreads();
-            }
-        }
-    }
     // last CTA out: the device-side bunch counter moves on; in data-parallel mode the step counter too, and every peer
     // learns that this rank no longer reads its factor arena (the peers' next pushes wait for that)
     if (threadIdx.x == 0 && gp->advance) {
@@ -378,7 +391,8 @@ int dw_wide_smem(int fblocks, int *op_stages, int *wd_stages)
     // Both streams are latency bound (bytes in flight per SM / round trip): the operand stream needs FB stages per segment at
     // ~1.9 us per ring round, the weight stream 204 MB through (stages x 16 KB) per ~2 us.  Measured on B200: 128-256 frames
     // are HBM bound (deep weight ring), 1024 frames operand bound (deep operand ring).
-    int ops = fblocks >= 32 ? 4 : (fblocks >= 16 ? 3 : 2);
+    // (2 weight stages at 1024 frames were a disaster: 260 us -- the weight stage cycle load -> update -> store is ~5 us)
+    int ops = fblocks >= 16 ? 3 : 2;
     int wds = (int)((224 * 1024 - ops * dww::OP_STAGE) / dww::WD_STAGE);
     if (wds > dww::MAX_WDS) wds = dww::MAX_WDS;
     { const char *ev = getenv("GGD_WIDE_OPS"); if (ev && atoi(ev) >= 2 && atoi(ev) <= dww::MAX_OPS) { ops = atoi(ev); wds = (int)((224 * 1024 - ops * dww::OP_STAGE) / dww::WD_STAGE); if (wds > dww::MAX_WDS) wds = dww::MAX_WDS; } }

@@ -24,6 +24,8 @@ struct DwwLayer {
 struct DwwArgs {
     DwwLayer layer[10];       // in the order the kernel walks them: TOP layer first (its factors arrive first)
     int nlayers, total_slabs;
+    int ngroups;              // slab groups walked one after the other by every CTA (dw_wide.cu: SegIter)
+    int group_base[11];       // first slab of each group, then total_slabs
     StepCtl *ctl;
     int rows_per_bunch;
     int fblocks;              // frames of the whole (padded) minibatch / 32

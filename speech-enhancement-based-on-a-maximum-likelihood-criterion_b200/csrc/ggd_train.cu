@@ -344,6 +344,16 @@ static int build_plans(ggd_handle *h)
             base += ceil_div(ly.Np, 128) * d.k_slabs;
         }
         a->total_slabs = base;
+        // slab groups: one GPU = one group; data parallel = {all layers above the bottom one}, {bottom layer} (its factors arrive last)
+        { const char *ev = getenv("GGD_WIDE_GROUPS");     // tuning: 0 = one group, 1 = one group per layer
+          const int mode = ev ? atoi(ev) : -1;
+          a->ngroups = 0;
+          a->group_base[a->ngroups++] = 0;
+          for (int i = 1; i < a->nlayers; i++) {
+              const bool cut = mode == 1 || (mode == -1 && h->dp_fx && i == a->nlayers - 1);
+              if (cut) a->group_base[a->ngroups++] = a->layer[i].slab_base;
+          }
+          a->group_base[a->ngroups] = base; }
         a->ctl = h->ctl; a->rows_per_bunch = h->M; a->fblocks = h->fx_rows / 32; a->rows = h->fx_rows;
         h->wide_smem = dw_wide_smem(a->fblocks, &a->op_stages, &a->wd_stages);
         a->mom = h->cfg.momentum; a->lr = h->cfg.lrate; a->Mg = (float)h->Mg;
@@ -485,7 +495,9 @@ static int fx_push(ggd_handle *h, cudaStream_t s, int event, SideCtx *sc, int *l
     cudaStream_t side;
     GGD_TRY(fx_fork(h, s, sc, &side));
     ProfScope ps(h, KC_PUSH, side);
-    launch_factor_push(h->fx_push[event], h->fx_push_ctas, side); (*launches)++;
+    // the LAST push of a step (dE/dx of the bottom layer) runs alone after the backward chain and is on the critical path: more CTAs
+    const int grid = (event == FX_EV_DX + 1) ? std::min(h->sm_count, 2 * h->fx_push_ctas) : h->fx_push_ctas;
+    launch_factor_push(h->fx_push[event], grid, side); (*launches)++;
     return GGD_OK;
 }
 

@@ -137,9 +137,11 @@ __device__ __forceinline__ float pow_abs(float a, float p)
     return (a > 0.0f) ? exp2f(p * __log2f(a)) : 0.0f;
 }
 
-constexpr int LOSS_COLS = 32;   // columns per block (one warp-wide coalesced row segment)
-constexpr int LOSS_ROWL = 32;   // row lanes per block (1024 threads)
-constexpr int LOSS_RMAX = 8;    // errors kept in registers per thread (bunches up to 256 frames make one pass over memory)
+constexpr int LOSS_COLS = 16;   // columns per block (64-byte row segments): 17 blocks for 257 outputs instead of 9 -- the kernel is
+                                // latency bound (9 blocks of 32 columns took 39 us at 1024 frames)
+constexpr int LOSS_ROWL = 64;   // row lanes per block (1024 threads)
+constexpr int LOSS_RMAX = 16;   // errors kept in registers per thread (bunches up to 1024 frames make one pass over memory)
+static_assert(LOSS_COLS == 16, "the alpha exchange uses one flag per 16-column block (FX_EV_LOSS + block), like the fused epilogue");
 
 __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
 {
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
                     if (live)
                         for (int p = 0; p < a.world; p++) a.asum_slot[p][(size_t)a.rank * a.D + d] = s_col[tx];
                     __threadfence_system();
-                    __syncwarp();
+                    __syncwarp(0x0000ffffu);
                     if (tx == 0)
                         for (int p = 0; p < a.world; p++)
                             if (p != a.rank) st_relaxed_sys_u32(a.lflags[p] + a.rank * FX_STRIDE + FX_EV_LOSS + blockIdx.x, step);   // (fenced above)
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
                             __nanosleep(32);
                         }
                     }
-                    __syncwarp();
+                    __syncwarp(0x0000ffffu);
                     if (live) {
                         float t = 0.0f;
                         for (int p = 0; p < a.world; p++) t += ld_relaxed_sys_f32(a.asum_slot[a.rank] + (size_t)p * a.D + d);   // rank order
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(LOSS_COLS *LOSS_ROWL) loss_kernel(LossArgs a)
         s_pa[tx] = pa;
         if (a.trace) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            for (int o = 8; o > 0; o >>= 1) contrib += __shfl_xor_sync(0x0000ffffu, contrib, o);     // ty == 0: lanes 0..15
             if (tx == 0) atomicAdd(a.trace + bunch, (double)contrib);
         }
     }
