@@ -416,7 +416,7 @@ def main():
     net = pkg.BP_GPU(0, local_rank, len(ls), ls, bunch, LR, MOM, WC, W, b, beta, ml, precision=prec, world_size=world, rank=rank,
                      nccl_unique_id=uid)
     # warm-up: at least 32 steps so that BOTH step graphs (16-step and single-step) have been uploaded and replayed once
-    K, Wm = args.steps, max(args.warmup, 35)      # 2 x 16-step graph + 3 single-step graphs
+    K, Wm = args.steps, max(args.warmup, 39)      # 2 x 16-step graph + 1 x 4-step graph + 3 single-step graphs: every graph uploaded
     nfr = K * bunch
     g = torch.Generator(device=dev); g.manual_seed(1 + rank)
     d_in = torch.randn(max(nfr, Wm * bunch), ls[0], device=dev, generator=g)        # synthetic frames, resident in HBM

@@ -112,7 +112,7 @@ struct ggd_handle {
     int wide_smem;
     unsigned int *dwp_counter;
     unsigned int *hang_host, *hang_dev;   // host-mapped record written by a device-side watchdog before it traps
-    cudaGraphExec_t g1, gN;
+    cudaGraphExec_t g1, g4, gN;     // step graphs of 1, 4 and 16 bunches (a chunk is 16a + 4b + c bunches)
     int gN_steps;
     int launches_per_step;
     // data parallelism
@@ -162,6 +162,7 @@ static void free_chunk(ggd_handle *h)
     h->cap = 0;
     if (h->g1) { cudaGraphExecDestroy(h->g1); h->g1 = nullptr; }
     if (h->gN) { cudaGraphExecDestroy(h->gN); h->gN = nullptr; }
+    if (h->g4) { cudaGraphExecDestroy(h->g4); h->g4 = nullptr; }
 }
 
 // Tile width and cluster split of one GEMM.  Measured on B200 (tools/gemm_probe.py): an SM pulls ~100 GB/s through
@@ -724,6 +725,7 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     const bool graphs = !(h->cfg.flags & GGD_FLAG_NO_GRAPH);
     if (graphs && !h->g1) {
         GGD_TRY(capture_graph(h, 1, &h->g1));
+        GGD_TRY(capture_graph(h, 4, &h->g4));
         h->gN_steps = 16;
         GGD_TRY(capture_graph(h, h->gN_steps, &h->gN));
     }
@@ -754,6 +756,7 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
         } else {
             int b = b0;
             for (; b + h->gN_steps <= b1; b += h->gN_steps) GGD_CUDA(cudaGraphLaunch(h->gN, h->s_main));
+            for (; b + 4 <= b1; b += 4) GGD_CUDA(cudaGraphLaunch(h->g4, h->s_main));
             for (; b < b1; b++) GGD_CUDA(cudaGraphLaunch(h->g1, h->s_main));
         }
     }
@@ -983,6 +986,7 @@ int ggd_reserve(ggd_handle *h, int n_frames)
     if (!(h->cfg.flags & GGD_FLAG_NO_GRAPH) && !h->g1) {
         GGD_TRY(set_ctl(h, h->c_in, h->c_targ));
         GGD_TRY(capture_graph(h, 1, &h->g1));
+        GGD_TRY(capture_graph(h, 4, &h->g4));
         h->gN_steps = 16;
         GGD_TRY(capture_graph(h, h->gN_steps, &h->gN));
     }

@@ -484,6 +484,22 @@ int bph_read_chunk_raw(void *p, int idx, unsigned *fea, unsigned *targ, int *fir
     memcpy(first, f.data(), f.size() * sizeof(int));
     return n;
 }
+// data-parallel view: the records of rank `rank`'s slice of chunk idx and the (rank-independent) row map
+int bph_read_chunk_raw_slice(void *p, int idx, int rank, int world, unsigned *fea, unsigned *targ, int *first, int max_frames, int *need, int *rec0, int *nrec)
+{
+    bphost::Host *h = (bphost::Host *)p;
+    unsigned *fb = nullptr, *tb = nullptr;
+    size_t fc = 0, tc = 0;
+    std::vector<int> f;
+    const int n = h->read_chunk_raw_slice(idx, rank, world, &fb, &fc, &tb, &tc, malloc, free, f, need, rec0, nrec);
+    if (n >= 0 && *nrec <= max_frames) {
+        memcpy(fea, fb, (size_t)*nrec * (2 + h->p.fea_dim) * sizeof(unsigned));
+        memcpy(targ, tb, (size_t)*nrec * (2 + h->p.layersizes[h->p.numlayers - 1]) * sizeof(unsigned));
+        memcpy(first, f.data(), f.size() * sizeof(int));
+    }
+    free(fb); free(tb);
+    return (n >= 0 && *nrec <= max_frames) ? n : -1;
+}
 const float *bph_weights(void *p, int l) { return ((bphost::Host *)p)->W[l].data(); }
 const float *bph_bias(void *p, int l) { return ((bphost::Host *)p)->b[l].data(); }
 int bph_write_weights(void *p) { return ((bphost::Host *)p)->write_weights() ? 0 : -1; }

@@ -91,6 +91,7 @@ def _host_lib():
     L.bph_shuffle.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
     L.bph_read_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, oracle_PF, oracle_PF]
     L.bph_read_chunk_raw.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    L.bph_read_chunk_raw_slice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 3
     L.bph_weights.restype = oracle_PF
     L.bph_weights.argtypes = [C.c_void_p, C.c_int]
     L.bph_write_weights.argtypes = [C.c_void_p]
@@ -389,3 +390,60 @@ def test_frame_expand_matches_reference_loops():
                 parts.append(f[T - 1] if t + c >= T else f[t + c - 1])
             rows.append(np.concatenate(parts))
         assert np.array_equal(O.frame_expand(f, ctx), np.stack(rows))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("traincache", [102400, 500])
+def test_host_loader_record_slices(oracle, tmp_path, world, traincache):
+    """data-parallel loader (host/interface.cpp read_chunk_raw_slice, ggd_raw_chunk::rec_frame0): every rank reads only its
+    1/world of a chunk's pfile records; the slices tile the chunk exactly (what the library's all-gather reassembles) and
+    every rank builds the SAME row -> first-frame map as the one-GPU loader (same lrand48 stream)"""
+    L = _host_lib()
+    ls = [1799, 32, 16, 257]
+    W, b = oracle.init_weights(ls, seed=3)
+    init = str(tmp_path / "init.wts")
+    oracle.write_wts(init, ls, W, b)
+    kw = _flags(tmp_path, init, traincache=traincache)
+    hosts = [L.bph_create(*_argv(kw)) for _ in range(world + 1)]        # hosts[world] = the one-GPU loader
+    assert all(hosts)
+    nch, ns = C.c_int(), C.c_int()
+    for h in hosts:
+        assert L.bph_chunk_info(h, b"0-7", 0, C.byref(nch), C.byref(ns)) == 0
+    maxf = 4096
+    for ci in range(nch.value):
+        full_f = np.zeros((maxf, 259), np.uint32); full_t = np.zeros((maxf, 259), np.uint32); full_first = np.zeros(traincache, np.int32)
+        need = C.c_int()
+        n = L.bph_read_chunk_raw(hosts[world], ci, full_f.ctypes.data, full_t.ctypes.data, full_first.ctypes.data, maxf, C.byref(need))
+        assert n > 0
+        S = -(-need.value // world)
+        got_f = np.zeros_like(full_f); got_t = np.zeros_like(full_t)
+        covered = 0
+        for r in range(world):
+            f = np.zeros((maxf, 259), np.uint32); t = np.zeros((maxf, 259), np.uint32); first = np.zeros(traincache, np.int32)
+            nd, r0, nr = C.c_int(), C.c_int(), C.c_int()
+            m = L.bph_read_chunk_raw_slice(hosts[r], ci, r, world, f.ctypes.data, t.ctypes.data, first.ctypes.data, maxf, C.byref(nd), C.byref(r0), C.byref(nr))
+            assert m == n and nd.value == need.value
+            assert r0.value == r * S and nr.value == max(0, min(S, need.value - r * S))
+            assert np.array_equal(first[:n], full_first[:n])
+            got_f[r0.value:r0.value + nr.value] = f[:nr.value]; got_t[r0.value:r0.value + nr.value] = t[:nr.value]
+            covered += nr.value
+        assert covered == need.value
+        assert np.array_equal(got_f[:need.value], full_f[:need.value]) and np.array_equal(got_t[:need.value], full_t[:need.value])
+    for h in hosts:
+        L.bph_destroy(h)
+
+
+def test_bench_reference_arm_uses_all_cores_under_torchrun_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the reference arm must still run the C oracle on every host core
+    and report the thread count it really used (VERDICT r1 weak #6)"""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--workload", "mmse_1799x2048x3_257_b128"], env=env, capture_output=True, text=True, timeout=600)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cores = len(os.sched_getaffinity(0))
+    assert line["impl"] == "reference" and line["cpu_baseline"]["cores"] == cores and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
