@@ -711,6 +711,16 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
 {
     const int nb = n_frames / h->M;   // trailing partial bunch dropped (BP_GPU.cu:173-180)
     const int PIECE = 16;             // bunches per upload piece (= the 16-step graph): 17 MB, 0.7 ms of PCIe under 1.8 ms of steps
+    // The first pieces are smaller (1, 1, 2, 4, 8 bunches) so that the first step waits for 1 MB, not 17 MB: a short chunk
+    // (bench --steps 20) otherwise spends a quarter of its time waiting for the first piece.
+    std::vector<int> pb;              // piece boundaries in bunches: piece p = bunches [pb[p], pb[p+1])
+    pb.push_back(0);
+    if (host_in != nullptr) {
+        for (int len = 1, first = 1; pb.back() < nb;) {
+            pb.push_back(std::min(nb, pb.back() + len));
+            if (first) first = 0; else if (len < PIECE) len *= 2;
+        }
+    } else pb.push_back(nb);
     const bool piped = host_in != nullptr;
     const int D_ = h->units[h->L - 1];
     h->stats.steps = nb; h->stats.launches = 0;
@@ -729,13 +739,13 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
         h->gN_steps = 16;
         GGD_TRY(capture_graph(h, h->gN_steps, &h->gN));
     }
-    const int npieces = piped ? ceil_div(nb, PIECE) : 1;
+    const int npieces = (int)pb.size() - 1;
     if (piped) {
         while ((int)h->ev_piece.size() < npieces) { cudaEvent_t e; GGD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_piece.push_back(e); }
         // the copy stream starts after everything queued so far on the compute stream (the previous chunk is done: calls are blocking)
         GGD_CUDA(cudaEventRecord(h->ev_c0, h->s_copy));
         for (int p = 0; p < npieces; p++) {
-            const size_t f0 = (size_t)p * PIECE * h->M, f1 = (p == npieces - 1) ? (size_t)n_frames : (size_t)(p + 1) * PIECE * h->M;
+            const size_t f0 = (size_t)pb[p] * h->M, f1 = (p == npieces - 1) ? (size_t)n_frames : (size_t)pb[p + 1] * h->M;
             GGD_CUDA(cudaMemcpyAsync(const_cast<float *>(d_in) + f0 * h->units[0], host_in + f0 * h->units[0], (f1 - f0) * h->units[0] * sizeof(float), cudaMemcpyHostToDevice, h->s_copy));
             GGD_CUDA(cudaMemcpyAsync(const_cast<float *>(d_targ) + f0 * D_, host_targ + f0 * D_, (f1 - f0) * D_ * sizeof(float), cudaMemcpyHostToDevice, h->s_copy));
             GGD_CUDA(cudaEventRecord(h->ev_piece[p], h->s_copy));
@@ -744,7 +754,7 @@ static int run_chunk(ggd_handle *h, int n_frames, const float *d_in, const float
     }
     int launches = 0;
     for (int p = 0; p < npieces; p++) {
-        const int b0 = piped ? p * PIECE : 0, b1 = piped ? std::min(nb, (p + 1) * PIECE) : nb;
+        const int b0 = pb[p], b1 = pb[p + 1];
         if (piped) GGD_CUDA(cudaStreamWaitEvent(h->s_main, h->ev_piece[p], 0));
         if (h->tensor && !presplit) {
             launch_split_rows(d_in + (size_t)b0 * h->M * h->units[0], (b1 - b0) * h->M, h->units[0], h->c_hi + (size_t)b0 * h->M * h->upad[0],
