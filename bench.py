@@ -468,6 +468,25 @@ def main():
                "h2d_bytes_per_step": int(s2["h2d_bytes"] // K), "d2h_bytes_per_step": int(max(s2["d2h_bytes"], 8 * K) // K),
                "h2d_ms": s2["h2d_ms"], "device_ms": s2["device_ms"]}
         del h_in, h_tg
+        # the drop-in's own path: PAGEABLE caller buffers (new float[] in Interface.cc:476-480) registered once by the library
+        # (GGD_FLAG_PIN_HOST), one GPU only: the second call over the same buffers is what an epoch's chunks see
+        if world == 1 and prec == 0:
+            try:
+                npg = min(nfr, 200 * bunch)
+                rs = np.random.RandomState(9)
+                pin_x = rs.standard_normal((npg, ls[0])).astype(np.float32); pin_t = rs.standard_normal((npg, ls[-1])).astype(np.float32)
+                net2 = pkg.BP_GPU(0, local_rank, len(ls), ls, bunch, LR, MOM, WC, W, b, beta, ml, flags=pkg.FLAG_PIN_HOST)
+                net2.keep_pinned(pin_x, pin_t)
+                net2.train(npg, pin_x, pin_t)             # registers the buffers, sizes the staging, uploads the graphs
+                t0 = time.perf_counter()
+                net2.train(npg, pin_x, pin_t)
+                _ = net2.losses()
+                dt2 = time.perf_counter() - t0
+                net2.close()
+                e2e["pageable_pin_host"] = {"value": npg / dt2, "unit": "frames/s", "frames": npg,
+                                            "what": "numpy (pageable) buffers + GGD_FLAG_PIN_HOST, second call over the same buffers"}
+            except Exception as ex:
+                e2e["pageable_pin_host"] = {"unavailable": str(ex)[:200]}
 
     # ---- per-kernel times (CUDA events around every launch, no graph) -> roofline of the dominant kernel
     peaks = measured_peaks()

@@ -1438,7 +1438,7 @@ int ggd_profile_kernels(ggd_handle *h, int n_frames, const float *d_in, const fl
 }
 
 // One training step with per-CTA phase stamps in every tensor-core kernel (tests / tuning only).
-// out[launch][12]: kind (0 fwd, 2 dx, 3 dw, 9 dw_update), ctas, first entry (us since the first kernel), last exit,
+// out[launch][12]: kind (0 fwd, 2 dx, 3 dw), ctas, first entry (us since the first kernel), last exit,
 // then medians of slots 1,2,3,4,6,7,8,9 relative to the CTA's own entry.
 int ggd_debug_trace_step(ggd_handle *h, const float *in, const float *targ, int fused, float *out, int max_launches, int *n_launches)
 {

@@ -1,4 +1,4 @@
-// pipe.cuh -- device helpers shared by the persistent TMA-pipelined kernels (dw_persist.cu, dp_push.cu):
+// pipe.cuh -- device helpers shared by the persistent TMA-pipelined kernels (dw_persist.cu, dw_wide.cu, dp_factor.cu):
 // bounded mbarrier waits with a host-visible watchdog record, TMEM loads, TMA stores and L2 cache policies.
 #pragma once
 #include "common.cuh"
