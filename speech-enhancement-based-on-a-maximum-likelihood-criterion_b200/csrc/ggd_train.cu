@@ -351,7 +351,8 @@ static int build_plans(ggd_handle *h)
           a->ngroups = 0;
           a->group_base[a->ngroups++] = 0;
           for (int i = 1; i < a->nlayers; i++) {
-              const bool cut = mode == 1 || (mode == -1 && h->dp_fx && i == a->nlayers - 1);
+              // (at 1024+ frames one contiguous range is better: fewer, wider segments outweigh the wait for the bottom layer)
+              const bool cut = mode == 1 || (mode == -1 && h->dp_fx && h->fx_rows < 1024 && i == a->nlayers - 1);
               if (cut) a->group_base[a->ngroups++] = a->layer[i].slab_base;
           }
           a->group_base[a->ngroups] = base; }
@@ -460,7 +461,9 @@ static int dp_fx_setup(ggd_handle *h)
     GGD_CUDA(cudaMemset(h->fx_flags, 0, (size_t)FX_MAX * FX_STRIDE * sizeof(unsigned int)));
     void *local[3] = {h->fx_arena, h->fx_asum, h->fx_flags};
     GGD_TRY(ipc_exchange(h, local, 3, h->fx_peer));
-    { const char *ev = getenv("GGD_FX_PUSH_CTAS"); h->fx_push_ctas = (ev && atoi(ev) > 0) ? atoi(ev) : 32 + 4 * (world - 2); }   // 32 CTAs per peer-MB is ample
+    { const char *ev = getenv("GGD_FX_PUSH_CTAS"); h->fx_push_ctas = (ev && atoi(ev) > 0) ? atoi(ev) : 32; }
+    // (32 CTAs at every N: the push CTAs' peer stores share the SMs' store paths with the GEMM epilogues -- at N = 8, 56 CTAs per
+    //  push slowed every GEMM of the chain from ~15 to ~21 us: 3.79 -> 4.17 M frames/s with 32)
     GGD_TRY(dp_barrier(h));    // nobody may enter the first step before every rank has mapped everyone
     return GGD_OK;
 }
