@@ -447,3 +447,52 @@ def test_bench_reference_arm_uses_all_cores_under_torchrun_env():
     cores = len(os.sched_getaffinity(0))
     assert line["impl"] == "reference" and line["cpu_baseline"]["cores"] == cores and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+
+
+def test_pfile_writer_reproduces_the_golden_pfile(oracle, tmp_path):
+    """host/pfile_writer.cpp (the container around the LPS kernel's pfile records: feacat + pfile_concat,
+    tools_pfile/pfile_noisy.pl:33,45): fed the records and sentence lengths of the reference's bundled train_noisy.pfile it
+    must reproduce that file byte for byte (header text, records, sentence table); the .norm writer reproduces qnnorm's
+    text layout (`vec N`, %g lines) and the bundled train_noisy.norm's numbers survive a round trip"""
+    L = _host_lib()
+    L.bph_write_pfile.argtypes = [C.c_char_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_int]
+    L.bph_write_norm.argtypes = [C.c_char_p, oracle_PF, oracle_PF, C.c_int]
+    gold = os.path.join(GOLDEN, "train_noisy.pfile")
+    blob = open(gold, "rb").read()
+    feats, tail, sent = oracle.read_pfile(gold)
+    nf = feats.shape[0]
+    rec = np.frombuffer(blob[32768:32768 + nf * 259 * 4], np.uint32).copy()
+    lens = np.diff(np.concatenate([[0], tail])).astype(np.int64)
+    assert lens.sum() == nf and len(lens) == 10
+    out = str(tmp_path / "mine.pfile")
+    assert L.bph_write_pfile(out.encode(), rec.ctypes.data, nf, 257, lens.ctypes.data, len(lens)) == 0
+    assert open(out, "rb").read() == blob
+    # a frame count that does not match the sentence table is refused
+    assert L.bph_write_pfile(out.encode(), rec.ctypes.data, nf - 1, 257, lens.ctypes.data, len(lens)) != 0
+    mean, dvar = oracle.read_norm(os.path.join(GOLDEN, "train_noisy.norm"), 257)
+    nout = str(tmp_path / "mine.norm")
+    assert L.bph_write_norm(nout.encode(), mean.ctypes.data_as(oracle_PF), dvar.ctypes.data_as(oracle_PF), 257) == 0
+    m2, d2 = oracle.read_norm(nout, 257)
+    assert np.array_equal(m2, mean) and np.array_equal(d2, dvar)
+    ref = str(tmp_path / "ref.norm")
+    oracle.write_norm(ref, mean, dvar)
+    assert open(nout).read() == open(ref).read()
+    assert open(nout).read().split("\n")[:3] == open(os.path.join(GOLDEN, "train_noisy.norm")).read().split("\n")[:3]
+
+
+def test_wav2pfile_fails_loudly_without_a_gpu(tmp_path):
+    """no CPU fallback: the fused PCM -> pfile tool exits non-zero with the library's message when no CUDA device exists"""
+    import subprocess
+    exe = os.path.join(PKG_DIR, "host", "Wav2Pfile")
+    if not os.path.exists(exe):
+        pytest.skip("host/Wav2Pfile not built")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    raw = str(tmp_path / "a.raw")
+    np.zeros(4000, np.int16).tofile(raw)
+    p = subprocess.run([exe, "-o", str(tmp_path / "a.pfile"), raw], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "CUDA" in p.stderr
