@@ -496,3 +496,32 @@ def test_wav2pfile_fails_loudly_without_a_gpu(tmp_path):
     np.zeros(4000, np.int16).tofile(raw)
     p = subprocess.run([exe, "-o", str(tmp_path / "a.pfile"), raw], capture_output=True, text=True, timeout=120)
     assert p.returncode != 0 and "CUDA" in p.stderr
+
+
+def test_enhance_tool_parses_files_and_fails_loudly_without_a_gpu(oracle, tmp_path):
+    """host/Enhance_LPS (decode.m's network part): .norm and MAT-v4 .wts are parsed and validated before the GPU is touched;
+    without a CUDA device it exits non-zero with the library's message (no CPU fallback)"""
+    import subprocess
+    exe = os.path.join(PKG_DIR, "host", "Enhance_LPS")
+    if not os.path.exists(exe):
+        pytest.skip("host/Enhance_LPS not built")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    ls = [7 * 257, 32, 257]
+    W, b = oracle.init_weights(ls, seed=2)
+    wts, nrm, lps = str(tmp_path / "m.wts"), str(tmp_path / "m.norm"), str(tmp_path / "a.lps")
+    oracle.write_wts(wts, ls, W, b)
+    mean, dvar = oracle.read_norm(os.path.join(GOLDEN, "train_noisy.norm"), 257)
+    oracle.write_norm(nrm, mean, dvar)
+    oracle.write_htk(lps, np.zeros((5, 257), np.float32))
+    base = [exe, "-wts", wts, "-norm", nrm, lps, str(tmp_path / "o.lps")]
+    p = subprocess.run(base + ["-layers", "1799,32,257"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "CUDA" in p.stderr, p.stderr            # files accepted, then no device
+    p = subprocess.run(base + ["-layers", "1799,33,257"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "expected" in p.stderr                  # .wts shape disagrees with -layers
+    p = subprocess.run(base + ["-layers", "1799,32,257", "-ctx", "5"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "context" in p.stderr
