@@ -15,6 +15,7 @@
 #include "dp_factor.cuh"
 #include <nccl.h>
 #include <stdarg.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -967,6 +968,25 @@ int ggd_destroy(ggd_handle *h)
     cudaSetDevice(h->cfg.gpu);
     if (h->s_main) cudaStreamSynchronize(h->s_main);
     if (h->s_copy) { cudaStreamSynchronize(h->s_copy); cudaStreamDestroy(h->s_copy); }
+    if (h->dp_fx && h->fx_flags && h->fx_counters && h->fx_peer[0][h->cfg.rank]) {
+        // Quiesce before my buffers go away: the LAST write a peer makes into my memory is its DONE flag of my last step (raised
+        // by the last CTA of its update kernel, possibly a little after my own step has finished).  Bounded: a lost peer must
+        // not turn destruction into a hang.
+        unsigned int step = 0;
+        const int world = h->cfg.world_size;
+        if (cudaMemcpy(&step, h->fx_counters + FXC_STEP, sizeof step, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            std::vector<unsigned int> fl((size_t)world * FX_STRIDE);
+            for (int tries = 0; tries < 2000; tries++) {
+                if (cudaMemcpy(fl.data(), h->fx_flags, fl.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+                bool all = true;
+                for (int p = 0; p < world; p++)
+                    if (p != h->cfg.rank && (int)(fl[(size_t)p * FX_STRIDE + FX_EV_DONE] - step) < 0) all = false;
+                if (all) break;
+                usleep(1000);
+            }
+        }
+        cudaGetLastError();
+    }
     for (cudaEvent_t e : h->ev_piece) cudaEventDestroy(e);
     if (h->ev_c0) cudaEventDestroy(h->ev_c0);
     if (h->ev_c1) cudaEventDestroy(h->ev_c1);
